@@ -1,0 +1,107 @@
+"""CPU: pin the numpy oracle against fixtures produced by executing the reference itself
+(tests/golden/make_golden.py). CubePad + integer maps bit-exact; float maps <= 1e-6."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import c2e as oc2e
+from oracle import cubepad as ocp
+from oracle import e2c as oe2c
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_cubepad_index_maps_all(golden_meta, golden_small):
+    for key, info in golden_meta["cubepad_maps"].items():
+        m = ocp.index_map(info["H"], info["H"], info["pad"]).astype(np.int32)
+        assert list(m.shape) == info["shape"], key
+        assert sha(m) == info["sha256"], key
+        if key in golden_small.files:
+            np.testing.assert_array_equal(m, golden_small[key])
+
+
+def test_cubepad_kat(golden_meta):
+    for kat in golden_meta["cubepad_kat"]:
+        x = np.arange(int(np.prod(kat["shape"])), dtype=np.float32).reshape(kat["shape"])
+        y = ocp.cubepad(x, kat["pad"])
+        assert list(y.shape) == kat["out_shape"]
+        assert sha(y) == kat["sha256"]
+        assert float(y.astype(np.float64).sum()) == kat["sum"]
+
+
+def test_cubepad_worked_example():
+    # SURVEY.md §8c worked example, 4x4 p=1
+    x = np.arange(96, dtype=np.float32).reshape(6, 1, 4, 4)
+    y = ocp.cubepad(x, 1)[:, 0].astype(int)
+    assert y[0].tolist() == [[83, 83, 82, 81, 80, 80], [67, 0, 1, 2, 3, 48], [71, 4, 5, 6, 7, 52],
+                             [75, 8, 9, 10, 11, 56], [79, 12, 13, 14, 15, 60], [31, 31, 30, 29, 28, 28]]
+    assert y[5].tolist() == [[3, 3, 2, 1, 0, 0], [48, 80, 81, 82, 83, 67], [49, 84, 85, 86, 87, 66],
+                             [50, 88, 89, 90, 91, 65], [51, 92, 93, 94, 95, 64], [32, 32, 33, 34, 35, 35]]
+
+
+def test_cubepad_random_multigroup(golden_meta, golden_small):
+    info = golden_meta["cubepad_rand"]
+    x = np.random.default_rng(info["seed"]).standard_normal(info["shape"]).astype(np.float32)
+    y = ocp.cubepad(x, info["pad"])
+    np.testing.assert_array_equal(y, golden_small["cubepad_rand_12x5x6x6_p2-1-1-3"])
+
+
+def test_cubepad_errors():
+    with pytest.raises(ValueError):
+        ocp.cubepad(np.zeros((5, 1, 4, 4), np.float32), 1)
+    with pytest.raises(ValueError):
+        ocp.index_map(4, 5, 1)
+
+
+def test_e2c_maps_and_faces(golden_meta, golden_small):
+    for key, info in golden_meta["e2c"].items():
+        w, H, W = info["w"], info["H"], info["W"]
+        sx, sy = oe2c.fixed_maps(w, H, W, info["vfov"])
+        assert sha(np.concatenate([sx.reshape(-1), sy.reshape(-1)])) == info["sxsy_sha256"], key
+        img = np.random.default_rng(info["seed"]).random((H, W, 3), dtype=np.float32)
+        faces = oe2c.to_cube(img, sx, sy)
+        # cv2.remap fp32 result reproduced bit for bit
+        assert sha(faces) == info["faces_sha256"], key
+        if key + "_sx" in golden_small.files:
+            np.testing.assert_array_equal(sx, golden_small[key + "_sx"])
+            np.testing.assert_array_equal(sy, golden_small[key + "_sy"])
+            np.testing.assert_array_equal(faces, golden_small[key + "_faces"])
+            xs, ys = oe2c.build_maps(w, H, W, info["vfov"])
+            np.testing.assert_allclose(np.stack(xs), golden_small[key + "_inX"], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(np.stack(ys), golden_small[key + "_inY"], rtol=0, atol=1e-9)
+        else:
+            np.testing.assert_array_equal(faces[:, ::17, ::13, :], golden_small[key + "_faces_probe"])
+
+
+def test_e2c_pack_roundtrip():
+    sx, sy = oe2c.fixed_maps(16, 64, 128)
+    p = oe2c.pack_map(sx, sy)
+    assert p.dtype == np.uint32
+    np.testing.assert_array_equal((p >> 20) & 2047, sx >> 5)
+    np.testing.assert_array_equal((p >> 10) & 1023, sy >> 5)
+    np.testing.assert_array_equal((p >> 5) & 31, sx & 31)
+    np.testing.assert_array_equal(p & 31, sy & 31)
+
+
+def test_c2e_maps_and_output(golden_meta, golden_small):
+    for key, info in golden_meta["c2e"].items():
+        w, C = info["w"], info["C"]
+        face, coord = oc2e.build_maps(w)
+        assert sha(face.astype(np.int64))[:16] == info["face_sha256_16"], key
+        assert sha(coord.astype(np.float32))[:16] == info["coord32_sha256_16"], key
+        assert sha(coord) == info["coord64_sha256"], key       # float64 bit-for-bit
+        _, _, _, M = oc2e.sample_plan(coord, w)
+        assert M == info["M"]
+        cube = np.random.default_rng(info["seed"]).standard_normal((6, C, w, w)).astype(np.float32)
+        out = oc2e.to_equi(cube, face, coord)
+        assert abs(float(out.astype(np.float64).sum()) - info["out_sum"]) < 1e-2
+        if key + "_out" in golden_small.files:
+            np.testing.assert_array_equal(face.astype(np.int8), golden_small[key + "_face"])
+            ref = golden_small[key + "_out"]
+            assert out.shape == ref.shape
+            assert np.abs(out - ref).max() <= 4e-6, key   # tolerance: CPU grid_sample vs restatement
+        else:
+            assert np.abs(out[:, :, ::7, ::11] - golden_small[key + "_out_probe"]).max() <= 4e-6
