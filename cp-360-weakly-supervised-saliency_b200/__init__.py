@@ -1,0 +1,18 @@
+"""cp360_b200 — B200 (sm_100a) spherical-projection hot path of CP-360-Weakly-Supervised-Saliency.
+
+Host-side mirror of the reference's three operators, backed by libcp360.so (include/cp360.h):
+
+    CubePad / CubePadding / get_pad_size     model/cube_pad.py
+    Equi2Cube                                utils/equi_to_cube.py
+    Cube2Equi                                utils/cube_to_equi.py
+
+plus SphericalPipeline (pipeline.py), the batched, frame-sharded chain the benchmark measures.
+"""
+from . import _lib
+from ._build import build_library, LIB_PATH
+from .cube_pad import CubePad, CubePadding, get_pad_size, cubepad_forward, cubepad_index_map
+from .cube_to_equi import Cube2Equi
+from .equi_to_cube import Equi2Cube
+
+__all__ = ["CubePad", "CubePadding", "get_pad_size", "cubepad_forward", "cubepad_index_map",
+           "Equi2Cube", "Cube2Equi", "build_library", "LIB_PATH"]

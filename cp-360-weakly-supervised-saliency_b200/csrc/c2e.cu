@@ -1,0 +1,269 @@
+// Cube faces -> equirectangular for sm_100a — replaces Cube2Equi.to_equi_nn
+// (utils/cube_to_equi.py:37-66: per call 2 map uploads, 6 full-grid grid_sample passes and 6
+// boolean-mask scatters) with ONE pass over a per-resolution sampling plan built on the host
+// (cp360_c2e_build_plan): per output pixel the face id, the north-west tap and the four fp32
+// bilinear weights exactly as torch's grid_sample forms them. Out-of-face taps contribute 0
+// (padding_mode='zeros'), which is what blends the output toward 0 along the cube seams.
+//
+//   c2e_kernel       equi[B,C,2w,4w]; thread = output pixel, loops over a channel chunk
+//   c2e_max_kernel   sal[B,2w,4w] = max_c equi — the form every call site consumes
+//                    (test_temporal.py:82-84); per-thread running max over the chunk, warp-free
+//                    combine across chunks with an order-preserving integer atomic max
+//   c2e_small_kernel w <= 16: the 6 faces of a channel group are staged in shared memory by TMA
+//                    bulk copies; used by both variants
+//   c2e_bwd_kernel   bilinear scatter-add of the output gradient (training path)
+#include <algorithm>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace cp360 {
+
+struct Tap {
+  int face, y0, x0;
+};
+
+__device__ __forceinline__ Tap decode_tap(uint32_t t) {
+  Tap r;
+  r.face = (int)(t >> 28);
+  r.y0 = (int)((t >> 14) & 0x3fffu) - 1;
+  r.x0 = (int)(t & 0x3fffu) - 1;
+  return r;
+}
+
+// float max through integer atomics (order-preserving for non-NaN values)
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  v += 0.0f;   // -0.0 -> +0.0
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+constexpr int kC2eThreads = 256;
+
+// MODE 0: write equi[B,C,P]; MODE 1: channel max into sal[B,P]
+template <int MODE>
+__global__ void __launch_bounds__(kC2eThreads)
+c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
+           const float4* __restrict__ wts, float* __restrict__ out, int64_t B, int C, int w,
+           int ch_per_block) {
+  const int P = 8 * w * w, ww = w * w;
+  const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
+  if (pix >= P) return;
+  const Tap t = decode_tap(__ldg(taps + pix));
+  const float4 wt = __ldg(wts + pix);
+  const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
+  const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
+  const bool nw_ok = xw_ok && yn_ok, ne_ok = xe_ok && yn_ok, sw_ok = xw_ok && ys_ok,
+             se_ok = xe_ok && ys_ok;
+  const int o_nw = t.y0 * w + t.x0;
+  const int c_begin = blockIdx.y * ch_per_block, c_end = min(C, c_begin + ch_per_block);
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+    const float* src = cube + ((b * 6 + t.face) * C + c_begin) * (int64_t)ww + o_nw;
+    float best = -INFINITY;
+#pragma unroll 4
+    for (int c = c_begin; c < c_end; ++c, src += ww) {
+      float acc = 0.0f;                      // order of torch's grid_sampler CUDA kernel
+      if (nw_ok) acc = fmaf(__ldg(src), wt.x, acc);
+      if (ne_ok) acc = fmaf(__ldg(src + 1), wt.y, acc);
+      if (sw_ok) acc = fmaf(__ldg(src + w), wt.z, acc);
+      if (se_ok) acc = fmaf(__ldg(src + w + 1), wt.w, acc);
+      if (MODE == 0) __stcs(out + (b * C + c) * (int64_t)P + pix, acc);
+      else best = fmaxf(best, acc);
+    }
+    if (MODE == 1) atomic_max_float(out + b * (int64_t)P + pix, best);
+  }
+}
+
+// Small faces (w <= 16): stage the whole 6-face cube of a channel group in shared memory.
+// Block = (b, channel group). Threads own output pixels (P = 8w^2 <= 2048, looped), channels
+// are the inner loop, so the plan entry lives in registers and the cube is read from DRAM
+// exactly once through six bulk copies.
+constexpr int kC2eSmallThreads = 512;
+
+template <int MODE>
+__global__ void __launch_bounds__(kC2eSmallThreads)
+c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
+                 const float4* __restrict__ wts, float* __restrict__ out, int C, int w, int kch,
+                 int groups) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* cs = reinterpret_cast<float*>(smem_raw + 128);       // [6][kch][w*w]
+  const int P = 8 * w * w, ww = w * w;
+  const int b = blockIdx.x / groups, gidx = blockIdx.x - b * groups;
+  const int c0 = gidx * kch, kl = min(kch, C - c0);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    tma::mbar_init(bar, 1);
+    tma::fence_mbar_init();
+    const uint32_t bytes = (uint32_t)(kl * ww) * 4u;
+    tma::mbar_expect_tx(bar, 6u * bytes);
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      tma::bulk_load(cs + (size_t)f * kch * ww, cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
+  }
+  __syncthreads();
+  tma::mbar_wait(bar, 0);
+  for (int pix = tid; pix < P; pix += kC2eSmallThreads) {
+    const Tap t = decode_tap(__ldg(taps + pix));
+    const float4 wt = __ldg(wts + pix);
+    const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
+    const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
+    // clamp tap addresses into the face and zero the weight instead of branching per channel
+    const int xw = xw_ok ? t.x0 : 0, xe = xe_ok ? t.x0 + 1 : 0, yn = yn_ok ? t.y0 : 0,
+              ys = ys_ok ? t.y0 + 1 : 0;
+    const bool nw_ok = xw_ok && yn_ok, ne_ok = xe_ok && yn_ok, sw_ok = xw_ok && ys_ok,
+               se_ok = xe_ok && ys_ok;
+    const float* src = cs + (size_t)t.face * kch * ww;
+    const int o_nw = yn * w + xw, o_ne = yn * w + xe, o_sw = ys * w + xw, o_se = ys * w + xe;
+    float best = -INFINITY;
+    float* dst = out + ((int64_t)b * C + c0) * P + pix;
+#pragma unroll 4
+    for (int c = 0; c < kl; ++c, src += ww) {
+      float acc = 0.0f;
+      if (nw_ok) acc = fmaf(src[o_nw], wt.x, acc);
+      if (ne_ok) acc = fmaf(src[o_ne], wt.y, acc);
+      if (sw_ok) acc = fmaf(src[o_sw], wt.z, acc);
+      if (se_ok) acc = fmaf(src[o_se], wt.w, acc);
+      if (MODE == 0) __stcs(dst + (int64_t)c * P, acc);
+      else best = fmaxf(best, acc);
+    }
+    if (MODE == 1) atomic_max_float(out + (int64_t)b * P + pix, best);
+  }
+}
+
+__global__ void __launch_bounds__(kC2eThreads)
+c2e_bwd_kernel(const float* __restrict__ gequi, const uint32_t* __restrict__ taps,
+               const float4* __restrict__ wts, float* __restrict__ gcube, int64_t B, int C, int w,
+               int ch_per_block) {
+  const int P = 8 * w * w, ww = w * w;
+  const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
+  if (pix >= P) return;
+  const Tap t = decode_tap(__ldg(taps + pix));
+  const float4 wt = __ldg(wts + pix);
+  const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
+  const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
+  const int o_nw = t.y0 * w + t.x0;
+  const int c_begin = blockIdx.y * ch_per_block, c_end = min(C, c_begin + ch_per_block);
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+    float* dst = gcube + ((b * 6 + t.face) * C + c_begin) * (int64_t)ww + o_nw;
+    for (int c = c_begin; c < c_end; ++c, dst += ww) {
+      const float g = __ldg(gequi + (b * C + c) * (int64_t)P + pix);
+      if (xw_ok && yn_ok) atomicAdd(dst, g * wt.x);
+      if (xe_ok && yn_ok) atomicAdd(dst + 1, g * wt.y);
+      if (xw_ok && ys_ok) atomicAdd(dst + w, g * wt.z);
+      if (xe_ok && ys_ok) atomicAdd(dst + w + 1, g * wt.w);
+    }
+  }
+}
+
+static int check_common(const void* a, const void* taps, const void* wts, const void* o, int64_t B,
+                        int64_t C, int w) {
+  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0, CP360_ERR_BAD_ARG, "bad size");
+  CP360_CHECK_ARG(w <= 8191 && C <= 0x7fffffff, CP360_ERR_RANGE, "face width / channels too large");
+  if (B == 0 || C == 0) return CP360_OK;
+  CP360_CHECK_ARG(a && taps && wts && o, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG(((uintptr_t)wts % 16) == 0 && ((uintptr_t)a % 4) == 0 && ((uintptr_t)o % 4) == 0 &&
+                      ((uintptr_t)taps % 4) == 0, CP360_ERR_ALIGN,
+                  "weights must be 16 B aligned, tensors 4 B aligned");
+  return require_device();
+}
+
+// channel-group size for the shared-memory variant (0 = does not apply)
+static int small_plan(const void* cube, int64_t C, int w, size_t* smem) {
+  if (w > 16 || ((uintptr_t)cube % 16) != 0) return 0;
+  const int ww = w * w;
+  int q = 1;
+  while ((q * ww) % 4) q <<= 1;                       // 16 B granularity of the bulk copies
+  if (C % q) return 0;
+  int k = (int)((96 * 1024) / (6 * ww * 4));          // <= 96 KB per block
+  k = (int)std::min<int64_t>(k, C);
+  k -= k % q;
+  if (k < q) return 0;
+  *smem = 128 + (size_t)6 * k * ww * 4;
+  return k;
+}
+
+template <int MODE>
+static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts, float* out,
+                      int64_t B, int64_t C, int w, cudaStream_t st) {
+  const int P = 8 * w * w;
+  size_t smem = 0;
+  int k = small_plan(cube, C, w, &smem);
+  if (k > 0) {
+    // keep >= ~2 blocks per SM in flight: shrink the group if the grid would be too small
+    const int ww = w * w;
+    int q = 1;
+    while ((q * ww) % 4) q <<= 1;
+    while (k > 4 * q && B * ((C + k - 1) / k) < 2 * (int64_t)sm_count()) {
+      k = std::max(q, (k / 2) - ((k / 2) % q));
+    }
+    smem = 128 + (size_t)6 * k * ww * 4;
+    const int groups = (int)((C + k - 1) / k);
+    CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
+    auto kern = c2e_small_kernel<MODE>;
+    CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(B * groups), kC2eSmallThreads, smem, st>>>(
+        cube, taps, reinterpret_cast<const float4*>(wts), out, (int)C, w, k, groups);
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
+  int chb = MODE == 0 ? 8 : 32;
+  chb = (int)std::min<int64_t>(chb, C);
+  dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)((C + chb - 1) / chb),
+            (unsigned)std::min<int64_t>(B, 65535));
+  CP360_CHECK_ARG(grid.y <= 65535, CP360_ERR_RANGE, "too many channel chunks");
+  c2e_kernel<MODE><<<grid, kC2eThreads, 0, st>>>(cube, taps, reinterpret_cast<const float4*>(wts),
+                                                 out, B, (int)C, w, chb);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+}  // namespace cp360
+
+using namespace cp360;
+
+extern "C" {
+
+int cp360_c2e_fwd(const float* cube, const uint32_t* taps, const float* wts, float* equi, int64_t B,
+                  int64_t C, int w, void* stream) {
+  int rc = check_common(cube, taps, wts, equi, B, C, w);
+  if (rc != CP360_OK || B == 0 || C == 0) return rc;
+  return launch_c2e<0>(cube, taps, wts, equi, B, C, w, (cudaStream_t)stream);
+}
+
+int cp360_c2e_max_fwd(const float* cube, const uint32_t* taps, const float* wts, float* sal,
+                      int64_t B, int64_t C, int w, void* stream) {
+  int rc = check_common(cube, taps, wts, sal, B, C, w);
+  if (rc != CP360_OK || B == 0) return rc;
+  CP360_CHECK_ARG(C > 0, CP360_ERR_BAD_ARG, "channel max over zero channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = B * 8 * (int64_t)w * w;
+  fill_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st>>>(sal, n, -INFINITY);
+  CP360_LAUNCHED();
+  return launch_c2e<1>(cube, taps, wts, sal, B, C, w, st);
+}
+
+int cp360_c2e_bwd(const float* gequi, const uint32_t* taps, const float* wts, float* gcube,
+                  int64_t B, int64_t C, int w, void* stream) {
+  int rc = check_common(gequi, taps, wts, gcube, B, C, w);
+  if (rc != CP360_OK || B == 0 || C == 0) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = 8 * w * w;
+  CP360_CUDA_OK(cudaMemsetAsync(gcube, 0, (size_t)B * 6 * C * w * w * sizeof(float), st));
+  const int chb = (int)std::min<int64_t>(16, C);
+  dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)((C + chb - 1) / chb),
+            (unsigned)std::min<int64_t>(B, 65535));
+  CP360_CHECK_ARG(grid.y <= 65535, CP360_ERR_RANGE, "too many channel chunks");
+  c2e_bwd_kernel<<<grid, kC2eThreads, 0, st>>>(gequi, taps, reinterpret_cast<const float4*>(wts),
+                                               gcube, B, (int)C, w, chb);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+// CubePad for sm_100a — replaces CubePad.forward / CubePadding.forward of the reference
+// (model/cube_pad.py:28-42, :95-216): x[6N,C,H,W] -> y[6N,C,H+pt+pd,W+pl+pr].
+//
+// Pure data movement, HBM-bound: every input element is read once from DRAM and every output
+// element written once. Three kernels, picked by shape:
+//
+//   cubepad_cube_kernel   small planes (H <= 32): a tile is ALL SIX faces of k channels of one
+//                         cube. TMA bulk-loads the six k*H*W chunks into shared memory, the
+//                         padded planes (face + rotated/flipped neighbour edges) are assembled in
+//                         shared memory in output layout through a per-geometry lookup table, and
+//                         six TMA bulk stores write them out. DRAM traffic is exactly 1x.
+//   cubepad_band_kernel   large planes: a tile is a contiguous chunk of one output plane. TMA
+//                         bulk-loads the input rows it covers, threads walk the output chunk
+//                         (coalesced, 128 B-aligned), taking the interior from shared memory and
+//                         the halo (<= 6 % of elements for H >= 64) straight from L2, and the
+//                         chunk leaves through a TMA bulk store (or direct streaming stores).
+//   cubepad_generic_kernel any element size / shape / alignment; one gather per element.
+//
+// The geometry is the 4x6 affine plate table of cubepad_geom.h, identical for all kernels and
+// for the host-side index map exported to the parity tests.
+#include <algorithm>
+
+#include "common.cuh"
+#include "cubepad_geom.h"
+#include "tma.cuh"
+
+namespace cp360 {
+
+enum CubePadAlgo { ALGO_AUTO = 0, ALGO_GENERIC = 1, ALGO_BAND_STG = 2, ALGO_BAND_BULK = 3, ALGO_CUBE = 4 };
+
+// ------------------------------------------------------------------------------------------
+// generic: any element type
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+cubepad_generic_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n_planes, int C,
+                       const __grid_constant__ CubePadGeom g) {
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  const int64_t face_stride = (int64_t)C * HW;
+  for (int64_t plane = blockIdx.y; plane < n_planes; plane += gridDim.y) {
+    const int64_t nf = plane / C;
+    const int c = (int)(plane - nf * C);
+    const int f = (int)(nf % 6);
+    const T* cube = x + ((nf - f) * C + c) * HW;          // face 0 of this cube, channel c
+    T* out = y + plane * HoWo;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HoWo; e += gridDim.x * blockDim.x) {
+      const int oy = e / g.Wo, ox = e - oy * g.Wo;
+      int sf;
+      const int pix = cubepad_src(g, f, oy, ox, &sf);
+      out[e] = cube[sf * face_stride + pix];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// band kernel: 32-bit elements, TMA bulk in, (TMA bulk | streaming) out
+// ------------------------------------------------------------------------------------------
+constexpr int kBandThreads = 512;
+constexpr int kBandStages = 3;   // input ring
+constexpr int kBandOutBufs = 3;  // output ring (bulk-store variant)
+
+struct BandArgs {
+  const uint32_t* x;
+  uint32_t* y;
+  int64_t n_tiles;
+  int32_t C;
+  int32_t tiles_per_plane;
+  int32_t tile_elems;     // multiple of 32
+  int32_t in_cap_words;   // per-stage capacity of the input ring (multiple of 32)
+};
+
+struct BandTile {
+  int64_t plane;
+  int32_t c0, c1;         // output element range inside the plane
+  int32_t in_start, in_words;  // input element range inside the plane (16 B aligned)
+};
+
+__device__ __forceinline__ BandTile band_tile(const BandArgs& a, const CubePadGeom& g, int64_t t) {
+  BandTile b;
+  b.plane = t / a.tiles_per_plane;
+  const int chunk = (int)(t - b.plane * a.tiles_per_plane);
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  b.c0 = chunk * a.tile_elems;
+  b.c1 = min(b.c0 + a.tile_elems, HoWo);
+  const int oy_first = b.c0 / g.Wo, oy_last = (b.c1 - 1) / g.Wo;
+  int ya = min(max(oy_first - g.pt, 0), g.H);
+  int yb = min(max(oy_last - g.pt + 1, 0), g.H);
+  if (yb <= ya) { ya = min(ya, g.H - 1); yb = ya + 1; }   // chunk lies in pad rows only: keep the protocol uniform
+  b.in_start = (ya * g.W) & ~3;
+  const int in_end = min((yb * g.W + 3) & ~3, HW);
+  b.in_words = in_end - b.in_start;
+  return b;
+}
+
+template <bool kBulkStore>
+__global__ void __launch_bounds__(kBandThreads)
+cubepad_band_kernel(const BandArgs a, const __grid_constant__ CubePadGeom g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [kBandStages]
+  uint32_t* in_ring = reinterpret_cast<uint32_t*>(smem_raw + 128);
+  uint32_t* out_ring = in_ring + (size_t)kBandStages * a.in_cap_words;    // bulk variant only
+
+  const int tid = threadIdx.x;
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  const int64_t face_stride = (int64_t)a.C * HW;
+
+  if (tid == 0) {
+    for (int s = 0; s < kBandStages; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int64_t t, int s) {
+    const BandTile b = band_tile(a, g, t);
+    const uint32_t bytes = (uint32_t)b.in_words * 4u;
+    tma::mbar_expect_tx(&full[s], bytes);
+    tma::bulk_load(in_ring + (size_t)s * a.in_cap_words, a.x + b.plane * HW + b.in_start, bytes,
+                   &full[s]);
+  };
+
+  if (tid == 0) {
+    int64_t t = blockIdx.x;
+    for (int s = 0; s < kBandStages && t < a.n_tiles; ++s, t += gridDim.x) issue_load(t, s);
+  }
+
+  const int dy = kBandThreads / g.Wo, dx = kBandThreads - dy * g.Wo;
+  int64_t it = 0;
+  for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+    const int s = (int)(it % kBandStages);
+    const uint32_t parity = (uint32_t)((it / kBandStages) & 1);
+    const BandTile b = band_tile(a, g, t);
+    const int64_t nf = b.plane / a.C;
+    const int c = (int)(b.plane - nf * a.C);
+    const int f = (int)(nf % 6);
+    const uint32_t* __restrict__ cube = a.x + ((nf - f) * a.C + c) * HW;
+    const uint32_t* in_s = in_ring + (size_t)s * a.in_cap_words;
+    const int n = b.c1 - b.c0;
+    uint32_t* out_s = out_ring + (size_t)(it % kBandOutBufs) * a.tile_elems;
+    uint32_t* __restrict__ out_g = a.y + b.plane * HoWo + b.c0;
+
+    int oy = (b.c0 + tid) / g.Wo;
+    int ox = (b.c0 + tid) - oy * g.Wo;
+
+    tma::mbar_wait(&full[s], parity);
+
+    constexpr int U = 4;
+    for (int j0 = tid; j0 < n; j0 += U * kBandThreads) {
+      uint32_t v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int yy = oy - g.pt, xx = ox - g.pl;
+        if (j0 + u * kBandThreads < n) {
+          if ((unsigned)yy < (unsigned)g.H && (unsigned)xx < (unsigned)g.W) {
+            v[u] = in_s[yy * g.W + xx - b.in_start];
+          } else {
+            int sf;
+            const int pix = cubepad_src(g, f, oy, ox, &sf);
+            v[u] = __ldg(cube + sf * face_stride + pix);
+          }
+        }
+        ox += dx; oy += dy;
+        if (ox >= g.Wo) { ox -= g.Wo; ++oy; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * kBandThreads;
+        if (j < n) {
+          if (kBulkStore) out_s[j] = v[u];
+          else __stcs(out_g + j, v[u]);
+        }
+      }
+    }
+
+    if (kBulkStore) {
+      tma::fence_proxy_async_smem();
+      // out buffer of tile it+1 was last used by the store of tile it+1-kBandOutBufs = it-2:
+      // allow only the most recent store (it-1) to be still reading shared memory.
+      if (tid == 0) tma::bulk_wait_read<kBandOutBufs - 2>();
+    }
+    __syncthreads();   // in_ring[s] fully consumed; out_s fully written; next out buffer free
+    if (tid == 0) {
+      if (kBulkStore) {
+        tma::bulk_store(out_g, out_s, (uint32_t)n * 4u);
+        tma::bulk_commit();
+      }
+      const int64_t tn = t + (int64_t)kBandStages * gridDim.x;
+      if (tn < a.n_tiles) issue_load(tn, s);
+    }
+  }
+  if (kBulkStore && tid == 0) tma::bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// cube-tile kernel: 32-bit elements, whole cube (6 faces x k channels) resident in smem
+// ------------------------------------------------------------------------------------------
+constexpr int kCubeThreads = 256;
+constexpr int kCubeStages = 3;
+constexpr int kCubeOutBufs = 3;
+
+struct CubeArgs {
+  const uint32_t* x;
+  uint32_t* y;
+  int64_t n_tiles;
+  int32_t C;
+  int32_t k;         // channels per tile
+  int32_t cblocks;   // ceil(C / k)
+};
+
+__global__ void __launch_bounds__(kCubeThreads)
+cubepad_cube_kernel(const CubeArgs a, const __grid_constant__ CubePadGeom g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  const int n_lut = 6 * HoWo;
+  const int in_words = 6 * a.k * HW, out_words = 6 * a.k * HoWo;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                       // [kCubeStages]
+  uint32_t* in_ring = reinterpret_cast<uint32_t*>(smem_raw + 128);
+  uint32_t* out_ring = in_ring + (size_t)kCubeStages * in_words;
+  uint16_t* lut_src = reinterpret_cast<uint16_t*>(out_ring + (size_t)kCubeOutBufs * out_words);
+  uint16_t* lut_dst = lut_src + ((n_lut + 7) & ~7);
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kCubeStages; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_mbar_init();
+  }
+  // lookup table: output element e = f*HoWo + oy*Wo + ox of channel 0  ->
+  //   source word inside the staged cube (face stride k*HW) / destination word (face stride k*HoWo)
+  for (int e = tid; e < n_lut; e += kCubeThreads) {
+    const int f = e / HoWo, r = e - f * HoWo;
+    const int oy = r / g.Wo, ox = r - oy * g.Wo;
+    int sf;
+    const int pix = cubepad_src(g, f, oy, ox, &sf);
+    lut_src[e] = (uint16_t)(sf * a.k * HW + pix);
+    lut_dst[e] = (uint16_t)(f * a.k * HoWo + r);
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int64_t t, int s) {
+    const int64_t grp = t / a.cblocks;
+    const int c0 = (int)(t - grp * a.cblocks) * a.k;
+    const int kl = min(a.k, a.C - c0);
+    const uint32_t bytes = (uint32_t)(kl * HW) * 4u;
+    tma::mbar_expect_tx(&full[s], 6u * bytes);
+    uint32_t* dst = in_ring + (size_t)s * in_words;
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      tma::bulk_load(dst + f * a.k * HW, a.x + ((grp * 6 + f) * a.C + c0) * HW, bytes, &full[s]);
+  };
+
+  if (tid == 0) {
+    int64_t t = blockIdx.x;
+    for (int s = 0; s < kCubeStages && t < a.n_tiles; ++s, t += gridDim.x) issue_load(t, s);
+  }
+
+  int64_t it = 0;
+  for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+    const int s = (int)(it % kCubeStages);
+    const uint32_t parity = (uint32_t)((it / kCubeStages) & 1);
+    const int64_t grp = t / a.cblocks;
+    const int c0 = (int)(t - grp * a.cblocks) * a.k;
+    const int kl = min(a.k, a.C - c0);
+    const uint32_t* in_s = in_ring + (size_t)s * in_words;
+    uint32_t* out_s = out_ring + (size_t)(it % kCubeOutBufs) * out_words;
+
+    tma::mbar_wait(&full[s], parity);
+
+    for (int e = tid; e < n_lut; e += kCubeThreads) {
+      const uint32_t* src = in_s + lut_src[e];
+      uint32_t* dst = out_s + lut_dst[e];
+      int cc = 0;
+      for (; cc + 4 <= kl; cc += 4) {
+        const uint32_t v0 = src[(cc + 0) * HW], v1 = src[(cc + 1) * HW];
+        const uint32_t v2 = src[(cc + 2) * HW], v3 = src[(cc + 3) * HW];
+        dst[(cc + 0) * HoWo] = v0; dst[(cc + 1) * HoWo] = v1;
+        dst[(cc + 2) * HoWo] = v2; dst[(cc + 3) * HoWo] = v3;
+      }
+      for (; cc < kl; ++cc) dst[cc * HoWo] = src[cc * HW];
+    }
+
+    tma::fence_proxy_async_smem();
+    if (tid == 0) tma::bulk_wait_read<kCubeOutBufs - 2>();
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(kl * HoWo) * 4u;
+#pragma unroll
+      for (int f = 0; f < 6; ++f)
+        tma::bulk_store(a.y + ((grp * 6 + f) * a.C + c0) * HoWo, out_s + f * a.k * HoWo, bytes);
+      tma::bulk_commit();
+      const int64_t tn = t + (int64_t)kCubeStages * gridDim.x;
+      if (tn < a.n_tiles) issue_load(tn, s);
+    }
+  }
+  if (tid == 0) tma::bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (fp32): interior copy, then halo scatter-add
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cubepad_bwd_interior_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t n_planes,
+                            const __grid_constant__ CubePadGeom g) {
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  for (int64_t plane = blockIdx.y; plane < n_planes; plane += gridDim.y) {
+    const float* src = gy + plane * HoWo + g.pt * g.Wo + g.pl;
+    float* dst = gx + plane * HW;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HW; e += gridDim.x * blockDim.x) {
+      const int yy = e / g.W, xx = e - yy * g.W;
+      dst[e] = src[yy * g.Wo + xx];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cubepad_bwd_halo_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t n_planes,
+                        int C, const __grid_constant__ CubePadGeom g) {
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  const int n_top = g.pt * g.Wo, lr = g.pl + g.pr, n_mid = g.H * lr;
+  const int n_halo = HoWo - HW;
+  const int64_t face_stride = (int64_t)C * HW;
+  for (int64_t plane = blockIdx.y; plane < n_planes; plane += gridDim.y) {
+    const int64_t nf = plane / C;
+    const int c = (int)(plane - nf * C);
+    const int f = (int)(nf % 6);
+    float* cube = gx + ((nf - f) * C + c) * HW;
+    const float* src = gy + plane * HoWo;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < n_halo; h += gridDim.x * blockDim.x) {
+      int oy, ox;
+      if (h < n_top) {
+        oy = h / g.Wo; ox = h - oy * g.Wo;
+      } else if (h < n_top + n_mid) {
+        const int q = h - n_top, r = q / lr, cc = q - r * lr;
+        oy = g.pt + r; ox = cc < g.pl ? cc : g.W + cc;
+      } else {
+        const int q = h - n_top - n_mid, r = q / g.Wo;
+        oy = g.pt + g.H + r; ox = q - r * g.Wo;
+      }
+      int sf;
+      const int pix = cubepad_src(g, f, oy, ox, &sf);
+      atomicAdd(cube + sf * face_stride + pix, src[oy * g.Wo + ox]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------
+static int smallest_k_quantum(int HW, int HoWo) {
+  for (int k = 1; k <= 4; k <<= 1)
+    if ((k * HW) % 4 == 0 && (k * HoWo) % 4 == 0) return k;
+  return 4;
+}
+
+template <typename T>
+static int launch_generic(const void* x, void* y, int64_t n_planes, int C, const CubePadGeom& g,
+                          cudaStream_t st) {
+  const int HoWo = g.Ho * g.Wo;
+  dim3 grid((unsigned)std::min(64, (HoWo + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
+  cubepad_generic_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (T*)y, n_planes, C, g);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+static bool cube_plan(const CubePadGeom& g, int C, int* k_out, size_t* smem_out) {
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  if (((int64_t)C * HW) % 4 || ((int64_t)C * HoWo) % 4) return false;
+  const int kq = smallest_k_quantum(HW, HoWo);
+  if (C % kq) return false;
+  const size_t lut = 2 * (size_t)((6 * HoWo + 7) & ~7) * sizeof(uint16_t);
+  auto total = [&](int k) {
+    return 128 + (size_t)(kCubeStages * 6 * k * HW + kCubeOutBufs * 6 * k * HoWo) * 4 + lut;
+  };
+  auto fits16 = [&](int k) { return 6 * k * HoWo <= 65535 && 6 * k * HW <= 65535; };
+  int best = 0;
+  for (int k = kq; k <= C && k <= 64; k += kq)
+    if (total(k) <= 100 * 1024 && fits16(k)) best = k;
+  if (!best && total(kq) <= 220 * 1024 && fits16(kq)) best = kq;
+  if (!best) return false;
+  *k_out = best;
+  *smem_out = total(best);
+  return true;
+}
+
+static int launch_cube(const void* x, void* y, int64_t n_faces, int C, const CubePadGeom& g,
+                       cudaStream_t st) {
+  int k; size_t smem;
+  CP360_CHECK_ARG(cube_plan(g, C, &k, &smem), CP360_ERR_SHAPE,
+                  "cube-tile kernel does not apply to H=%d C=%d", g.H, C);
+  CubeArgs a;
+  a.x = (const uint32_t*)x; a.y = (uint32_t*)y; a.C = C; a.k = k; a.cblocks = (C + k - 1) / k;
+  a.n_tiles = (n_faces / 6) * a.cblocks;
+  CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_cube_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
+  cubepad_cube_kernel<<<(unsigned)grid, kCubeThreads, smem, st>>>(a, g);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+static bool band_ok(const CubePadGeom& g) {
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  return HW % 4 == 0 && HoWo % 4 == 0 && g.Wo <= kBandThreads;
+}
+
+static int launch_band(const void* x, void* y, int64_t n_planes, int C, const CubePadGeom& g,
+                       bool bulk_store, cudaStream_t st) {
+  CP360_CHECK_ARG(band_ok(g), CP360_ERR_SHAPE, "band kernel does not apply to H=%d", g.H);
+  const int HoWo = g.Ho * g.Wo;
+  const int te_max = 4096;
+  const int tpp = (HoWo + te_max - 1) / te_max;
+  const int te = (((HoWo + tpp - 1) / tpp) + 31) & ~31;
+  BandArgs a;
+  a.x = (const uint32_t*)x; a.y = (uint32_t*)y; a.C = C;
+  a.tile_elems = te;
+  a.tiles_per_plane = (HoWo + te - 1) / te;
+  a.n_tiles = n_planes * a.tiles_per_plane;
+  const int rows = te / g.Wo + 3;
+  a.in_cap_words = ((rows * g.W + 8) + 31) & ~31;
+  const size_t smem = 128 + (size_t)kBandStages * a.in_cap_words * 4 +
+                      (bulk_store ? (size_t)kBandOutBufs * te * 4 : 0);
+  auto kern = bulk_store ? cubepad_band_kernel<true> : cubepad_band_kernel<false>;
+  CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
+  kern<<<(unsigned)grid, kBandThreads, smem, st>>>(a, g);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+static int validate(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
+                    int pr, int pt, int pd, CubePadGeom* g) {
+  CP360_CHECK_ARG(n_faces >= 0 && C >= 0, CP360_ERR_BAD_ARG, "negative size");
+  CP360_CHECK_ARG(n_faces % 6 == 0, CP360_ERR_GROUP, "CubePad size mismatch! batch %lld %% 6 != 0",
+                  (long long)n_faces);
+  CP360_CHECK_ARG(make_geom(H, W, pl, pr, pt, pd, g), CP360_ERR_SHAPE,
+                  "CubePad needs square faces and 0 <= pad <= H (H=%d W=%d pads l%d r%d t%d d%d)", H,
+                  W, pl, pr, pt, pd);
+  CP360_CHECK_ARG(C <= 0x7fffffff && (int64_t)6 * g->Ho * g->Wo < 0x7fffffff, CP360_ERR_SHAPE,
+                  "plane too large");
+  if (n_faces == 0 || C == 0) return CP360_OK;
+  CP360_CHECK_ARG(x && y, CP360_ERR_BAD_ARG, "null tensor pointer");
+  return CP360_OK;
+}
+
+}  // namespace cp360
+
+using namespace cp360;
+
+extern "C" {
+
+int cp360_cubepad_out_shape(int H, int W, int pl, int pr, int pt, int pd, int* Ho, int* Wo) {
+  CubePadGeom g;
+  CP360_CHECK_ARG(make_geom(H, W, pl, pr, pt, pd, &g), CP360_ERR_SHAPE,
+                  "CubePad needs square faces and 0 <= pad <= H");
+  if (Ho) *Ho = g.Ho;
+  if (Wo) *Wo = g.Wo;
+  return CP360_OK;
+}
+
+int cp360_cubepad_build_map(int H, int W, int pl, int pr, int pt, int pd, int32_t* map_host) {
+  CubePadGeom g;
+  CP360_CHECK_ARG(map_host, CP360_ERR_BAD_ARG, "null map pointer");
+  CP360_CHECK_ARG(make_geom(H, W, pl, pr, pt, pd, &g), CP360_ERR_SHAPE,
+                  "CubePad needs square faces and 0 <= pad <= H");
+  for (int f = 0; f < 6; ++f)
+    for (int oy = 0; oy < g.Ho; ++oy)
+      for (int ox = 0; ox < g.Wo; ++ox) {
+        int sf;
+        const int pix = cubepad_src(g, f, oy, ox, &sf);
+        map_host[(f * g.Ho + oy) * g.Wo + ox] = sf * H * W + pix;
+      }
+  return CP360_OK;
+}
+
+int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
+                           int pr, int pt, int pd, int elem_bytes, int algo, void* stream) {
+  CubePadGeom g;
+  int rc = validate(x, y, n_faces, C, H, W, pl, pr, pt, pd, &g);
+  if (rc != CP360_OK) return rc;
+  CP360_CHECK_ARG(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8 ||
+                      elem_bytes == 16,
+                  CP360_ERR_BAD_ARG, "elem_bytes must be 1,2,4,8 or 16 (got %d)", elem_bytes);
+  CP360_CHECK_ARG(((uintptr_t)x % elem_bytes) == 0 && ((uintptr_t)y % elem_bytes) == 0,
+                  CP360_ERR_ALIGN, "tensor pointer not aligned to the element size");
+  if (n_faces == 0 || C == 0) return CP360_OK;
+  rc = require_device();
+  if (rc != CP360_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_planes = n_faces * C;
+  const bool fast_ok = elem_bytes == 4 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
+
+  if (algo == ALGO_AUTO) {
+    int k; size_t smem;
+    if (fast_ok && H <= 32 && cube_plan(g, (int)C, &k, &smem)) algo = ALGO_CUBE;
+    else if (fast_ok && band_ok(g) && H >= 24) algo = ALGO_BAND_BULK;
+    else algo = ALGO_GENERIC;
+  }
+  switch (algo) {
+    case ALGO_CUBE:
+      CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "cube-tile kernel needs 4-byte elements, 16 B aligned");
+      return launch_cube(x, y, n_faces, (int)C, g, st);
+    case ALGO_BAND_STG:
+    case ALGO_BAND_BULK:
+      CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "band kernel needs 4-byte elements, 16 B aligned");
+      return launch_band(x, y, n_planes, (int)C, g, algo == ALGO_BAND_BULK, st);
+    case ALGO_GENERIC:
+      switch (elem_bytes) {
+        case 1: return launch_generic<uint8_t>(x, y, n_planes, (int)C, g, st);
+        case 2: return launch_generic<uint16_t>(x, y, n_planes, (int)C, g, st);
+        case 4: return launch_generic<uint32_t>(x, y, n_planes, (int)C, g, st);
+        case 8: return launch_generic<uint64_t>(x, y, n_planes, (int)C, g, st);
+        default: return launch_generic<uint4>(x, y, n_planes, (int)C, g, st);
+      }
+    default:
+      set_error("unknown CubePad algo %d", algo);
+      return CP360_ERR_BAD_ARG;
+  }
+}
+
+int cp360_cubepad_fwd(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
+                      int pr, int pt, int pd, int elem_bytes, void* stream) {
+  return cp360_cubepad_fwd_algo(x, y, n_faces, C, H, W, pl, pr, pt, pd, elem_bytes, ALGO_AUTO, stream);
+}
+
+int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C, int H, int W,
+                          int pl, int pr, int pt, int pd, void* stream) {
+  CubePadGeom g;
+  int rc = validate(gy, gx, n_faces, C, H, W, pl, pr, pt, pd, &g);
+  if (rc != CP360_OK) return rc;
+  if (n_faces == 0 || C == 0) return CP360_OK;
+  rc = require_device();
+  if (rc != CP360_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_planes = n_faces * C;
+  const int HW = g.H * g.W, n_halo = g.Ho * g.Wo - HW;
+  dim3 grid((unsigned)std::min(64, (HW + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
+  cubepad_bwd_interior_kernel<<<grid, 256, 0, st>>>(gy, gx, n_planes, g);
+  CP360_LAUNCHED();
+  if (n_halo > 0) {
+    dim3 grid2((unsigned)std::min(64, (n_halo + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
+    cubepad_bwd_halo_kernel<<<grid2, 256, 0, st>>>(gy, gx, n_planes, (int)C, g);
+    CP360_LAUNCHED();
+  }
+  return CP360_OK;
+}
+
+}  // extern "C"

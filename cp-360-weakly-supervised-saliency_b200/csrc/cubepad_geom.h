@@ -1,0 +1,130 @@
+// CubePad geometry as a 4x6 table of affine source maps (host + device).
+//
+// The reference builds the four padding plates of each face by slicing / transposing /
+// flipping a neighbouring face (model/cube_pad.py:114-162) and the corners by repeating a
+// plate edge (make_cubepad_edge, :83-90, :165-176). Every plate element is therefore
+//     src = (face', y', x')  with  y' = yr*r + yc*c + y0,   x' = xr*r + xc*c + x0
+// where (r, c) are the element's coordinates inside the plate and the coefficients depend only
+// on (plate, face, H, W, pads). The table is filled once per launch on the host and handed to
+// the kernels by value; the kernels never branch on the face id.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CP360_HD __host__ __device__ __forceinline__
+#else
+#define CP360_HD inline
+#endif
+
+namespace cp360 {
+
+enum Face { FB = 0, FD = 1, FF = 2, FL = 3, FR = 4, FT = 5 };
+enum Plate { P_TOP = 0, P_DOWN = 1, P_LEFT = 2, P_RIGHT = 3 };
+
+struct PlateMap {      // source = (face, pix) with pix = base + sr*r + sc*c  (pix = y'*W + x')
+  int32_t face;        // face'
+  int32_t base;        // y0*W + x0
+  int32_t sr;          // yr*W + xr
+  int32_t sc;          // yc*W + xc
+};
+
+struct CubePadGeom {
+  int32_t H, W, pl, pr, pt, pd, Ho, Wo;
+  int32_t corner_uses_lr[4];   // [tl, tr, dl, dr]: 1 -> corner repeats the l/r plate row, 0 -> t/d plate column
+  PlateMap plate[4][6];
+};
+
+// rows: what the reference slices for each face, written as (face', y(r,c), x(r,c)).
+// y = yr*r + yc*c + y0 ; x = xr*r + xc*c + x0
+struct AffineSrc { int face, yr, yc, y0, xr, xc, x0; };
+
+inline PlateMap make_plate(const AffineSrc& a, int H, int W) {
+  PlateMap m;
+  m.face = a.face;
+  m.base = a.y0 * W + a.x0;
+  m.sr = a.yr * W + a.xr;
+  m.sc = a.yc * W + a.xc;
+  return m;
+}
+
+// Fills the table. Returns false for shapes the reference cannot pad (H != W, pad > H, pad < 0).
+inline bool make_geom(int H, int W, int pl, int pr, int pt, int pd, CubePadGeom* g) {
+  if (H <= 0 || W <= 0 || H != W) return false;
+  if (pl < 0 || pr < 0 || pt < 0 || pd < 0) return false;
+  if (pl > W || pr > W || pt > H || pd > H) return false;
+  g->H = H; g->W = W; g->pl = pl; g->pr = pr; g->pt = pt; g->pd = pd;
+  g->Ho = H + pt + pd; g->Wo = W + pl + pr;
+  // top plate, r in [0,pt), c in [0,W)                      cube_pad.py:114-126
+  const AffineSrc top[6] = {
+      /*B*/ {FT, 1, 0, 0, 0, -1, W - 1},          // flip(top[:pt, :])
+      /*D*/ {FF, 1, 0, H - pt, 0, 1, 0},          // front[-pt:, :]
+      /*F*/ {FT, 1, 0, H - pt, 0, 1, 0},          // top[-pt:, :]
+      /*L*/ {FT, 0, 1, 0, 1, 0, 0},               // top[:, :pt]^T
+      /*R*/ {FT, 0, -1, H - 1, 1, 0, W - pt},     // flip(top[:, -pt:]^T)
+      /*T*/ {FB, 1, 0, 0, 0, -1, W - 1}};         // flip(back[:pt, :])
+  // down plate, r in [0,pd), c in [0,W)                     cube_pad.py:127-138
+  const AffineSrc down[6] = {
+      /*B*/ {FD, 1, 0, H - pd, 0, -1, W - 1},     // flip(down[-pd:, :])
+      /*D*/ {FB, 1, 0, H - pd, 0, -1, W - 1},     // flip(back[-pd:, :])
+      /*F*/ {FD, 1, 0, 0, 0, 1, 0},               // down[:pd, :]
+      /*L*/ {FD, 0, -1, H - 1, 1, 0, 0},          // flip(down[:, :pd]^T)
+      /*R*/ {FD, 0, 1, 0, 1, 0, W - pd},          // down[:, -pd:]^T
+      /*T*/ {FF, 1, 0, 0, 0, 1, 0}};              // front[:pd, :]
+  // left plate, r in [0,H), c in [0,pl)                     cube_pad.py:139-150
+  const AffineSrc left[6] = {
+      /*B*/ {FR, 1, 0, 0, 0, 1, W - pl},          // right[:, -pl:]
+      /*D*/ {FL, 0, 1, H - pl, -1, 0, W - 1},     // flip(left[-pl:, :]^T, rows)
+      /*F*/ {FL, 1, 0, 0, 0, 1, W - pl},          // left[:, -pl:]
+      /*L*/ {FB, 1, 0, 0, 0, 1, W - pl},          // back[:, -pl:]
+      /*R*/ {FF, 1, 0, 0, 0, 1, W - pl},          // front[:, -pl:]
+      /*T*/ {FL, 0, 1, 0, 1, 0, 0}};              // left[:pl, :]^T
+  // right plate, r in [0,H), c in [0,pr)                    cube_pad.py:151-162
+  const AffineSrc right[6] = {
+      /*B*/ {FL, 1, 0, 0, 0, 1, 0},               // left[:, :pr]
+      /*D*/ {FR, 0, 1, H - pr, 1, 0, 0},          // right[-pr:, :]^T
+      /*F*/ {FR, 1, 0, 0, 0, 1, 0},               // right[:, :pr]
+      /*L*/ {FF, 1, 0, 0, 0, 1, 0},               // front[:, :pr]
+      /*R*/ {FB, 1, 0, 0, 0, 1, 0},               // back[:, :pr]
+      /*T*/ {FR, 0, 1, 0, -1, 0, W - 1}};         // flip(right[:pr, :]^T, rows)
+  for (int f = 0; f < 6; ++f) {
+    g->plate[P_TOP][f] = make_plate(top[f], H, W);
+    g->plate[P_DOWN][f] = make_plate(down[f], H, W);
+    g->plate[P_LEFT][f] = make_plate(left[f], H, W);
+    g->plate[P_RIGHT][f] = make_plate(right[f], H, W);
+  }
+  // make_cubepad_edge: td_pad > lr_pad -> repeat the l/r plate's row, else the t/d plate's column
+  g->corner_uses_lr[0] = pt > pl;
+  g->corner_uses_lr[1] = pt > pr;
+  g->corner_uses_lr[2] = pd > pl;
+  g->corner_uses_lr[3] = pd > pr;
+  return true;
+}
+
+// Source of output pixel (oy, ox) of face f: returns the pixel offset y'*W + x' inside the
+// source face plane and writes the source face id to *src_face.
+CP360_HD int32_t cubepad_src(const CubePadGeom& g, int f, int oy, int ox, int* src_face) {
+  const int y = oy - g.pt, x = ox - g.pl;
+  const bool top = y < 0, bot = y >= g.H, lft = x < 0, rgt = x >= g.W;
+  if (!(top | bot | lft | rgt)) {
+    *src_face = f;
+    return y * g.W + x;
+  }
+  int plate, r, c;
+  if (!(lft | rgt)) {                       // top / down plate
+    plate = top ? P_TOP : P_DOWN; r = top ? oy : y - g.H; c = x;
+  } else if (!(top | bot)) {                // left / right plate
+    plate = lft ? P_LEFT : P_RIGHT; r = y; c = lft ? ox : x - g.W;
+  } else {                                  // corner
+    const int k = (bot ? 2 : 0) + (rgt ? 1 : 0);
+    if (g.corner_uses_lr[k]) {
+      plate = lft ? P_LEFT : P_RIGHT; r = top ? 0 : g.H - 1; c = lft ? ox : x - g.W;
+    } else {
+      plate = top ? P_TOP : P_DOWN; r = top ? oy : y - g.H; c = lft ? 0 : g.W - 1;
+    }
+  }
+  const PlateMap& m = g.plate[plate][f];
+  *src_face = m.face;
+  return m.base + m.sr * r + m.sc * c;
+}
+
+}  // namespace cp360

@@ -1,0 +1,123 @@
+"""CubePad — host mirror of the reference's model/cube_pad.py (same names, same arguments).
+
+    CubePad(lrtd_pad, use_gpu=True)            cube_pad.py:23-42
+    CubePadding(lrtd_pad, use_gpu=True)        cube_pad.py:45-216   (one 6-face group)
+    get_pad_size(lrtd_pad)                     cube_pad.py:12-20
+
+forward(x[6N,C,H,W]) -> [6N,C,H+p_t+p_d,W+p_l+p_r] runs ONE kernel launch of libcp360
+(cp360_cubepad_fwd) on the tensor's device and current stream, for the whole batch — the
+reference's per-group Python loop, ~41 ATen launches and 8 synchronous index uploads per group
+are gone. Differentiable (cp360_cubepad_bwd_f32) because temporal_model/train_temporal.py
+back-propagates through it. CPU tensors are rejected: there is no fallback path.
+"""
+import numbers
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def get_pad_size(lrtd_pad):
+    """int -> same pad on all sides; else [p_l, p_r, p_t, p_d] (cube_pad.py:12-20)."""
+    if isinstance(lrtd_pad, numbers.Integral):
+        p = int(lrtd_pad)
+        return p, p, p, p
+    p_l, p_r, p_t, p_d = (int(v) for v in lrtd_pad)
+    return p_l, p_r, p_t, p_d
+
+
+def cubepad_index_map(H, W, lrtd_pad):
+    """Host: int32 [6,Ho,Wo] source index (face*H*W + y*W + x) of every output pixel."""
+    import numpy as np
+    import ctypes
+    p_l, p_r, p_t, p_d = get_pad_size(lrtd_pad)
+    lib = _lib.lib()
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.cp360_cubepad_out_shape(H, W, p_l, p_r, p_t, p_d, ctypes.byref(ho), ctypes.byref(wo)))
+    m = np.empty((6, ho.value, wo.value), dtype=np.int32)
+    _lib.check(lib.cp360_cubepad_build_map(H, W, p_l, p_r, p_t, p_d, m.ctypes.data))
+    return m
+
+
+def _require_cuda(t, who):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s expects a torch.Tensor, got %s" % (who, type(t).__name__))
+    if not t.is_cuda:
+        raise RuntimeError("%s: tensor is on %s; this build runs only on CUDA (sm_100a) and has "
+                           "no CPU fallback" % (who, t.device))
+
+
+def cubepad_forward(x, pads, algo=_lib.ALGO_AUTO):
+    """Raw launch: x [6N,C,H,W] cuda -> new contiguous [6N,C,Ho,Wo]."""
+    _require_cuda(x, "CubePad")
+    if x.dim() != 4:
+        raise ValueError("CubePad expects [6N, C, H, W], got %s" % (tuple(x.shape),))
+    p_l, p_r, p_t, p_d = pads
+    n, c, h, w = x.shape
+    if n % 6 != 0:
+        # the reference prints this and calls exit() (cube_pad.py:33-35); an exception is kinder
+        raise ValueError("CubePad size mismatch! batch %d is not a multiple of 6" % n)
+    x = x.contiguous()
+    y = torch.empty((n, c, h + p_t + p_d, w + p_l + p_r), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().cp360_cubepad_fwd_algo(
+            x.data_ptr(), y.data_ptr(), n, c, h, w, p_l, p_r, p_t, p_d, x.element_size(), algo, st))
+    return y
+
+
+def cubepad_backward(gy, pads, in_hw):
+    _require_cuda(gy, "CubePad.backward")
+    p_l, p_r, p_t, p_d = pads
+    h, w = in_hw
+    n, c = gy.shape[0], gy.shape[1]
+    g32 = gy.contiguous() if gy.dtype == torch.float32 else gy.float().contiguous()
+    gx = torch.empty((n, c, h, w), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().cp360_cubepad_bwd_f32(
+            g32.data_ptr(), gx.data_ptr(), n, c, h, w, p_l, p_r, p_t, p_d, st))
+    return gx if gy.dtype == torch.float32 else gx.to(gy.dtype)
+
+
+class _CubePadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pads):
+        ctx.pads = pads
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        return cubepad_forward(x, pads)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return cubepad_backward(gy, ctx.pads, ctx.in_hw), None
+
+
+class CubePad(nn.Module):
+    """Drop-in for the reference's CubePad (cube_pad.py:23-42). No parameters or buffers."""
+
+    def __init__(self, lrtd_pad, use_gpu=True):
+        super().__init__()
+        if not use_gpu:
+            raise RuntimeError("CubePad(use_gpu=False): this build is CUDA-only (no CPU fallback)")
+        self.pads = get_pad_size(lrtd_pad)
+        self.p_l, self.p_r, self.p_t, self.p_d = self.pads
+
+    def forward(self, x):
+        """x [6N,C,H,W] -> [6N,C,H+p_t+p_d,W+p_l+p_r]; face order B,D,F,L,R,T per group of 6."""
+        if x.requires_grad and torch.is_grad_enabled():
+            return _CubePadFn.apply(x, self.pads)
+        return cubepad_forward(x, self.pads)
+
+    def extra_repr(self):
+        return "lrtd_pad=[%d, %d, %d, %d]" % self.pads
+
+
+class CubePadding(CubePad):
+    """The reference's inner module (cube_pad.py:45-216) padded exactly one 6-face group; the
+    kernel handles any number of groups, so this is the same operator under the old name."""
+
+    def forward(self, x):
+        if x.dim() == 4 and x.shape[0] != 6:
+            raise ValueError("CubePadding expects exactly 6 faces, got %d" % x.shape[0])
+        return super().forward(x)

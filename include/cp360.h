@@ -1,0 +1,159 @@
+/*
+ * cp360.h — C ABI of libcp360.so: the B200 (sm_100a) spherical-projection hot path of
+ * hsientzucheng/CP-360-Weakly-Supervised-Saliency.
+ *
+ * The reference is pure Python and has no FFI layer; its boundary for this path is three
+ * classes:
+ *     CubePad(lrtd_pad).forward(x)            model/cube_pad.py:23-42
+ *     Equi2Cube(w, img).to_cube(img)          utils/equi_to_cube.py:11-129
+ *     Cube2Equi(w).to_equi_nn(cube)           utils/cube_to_equi.py:11-66
+ * Each entry point below replaces the body of one of those methods (file:line cited per
+ * function). A maintainer binds them with ctypes; the host mirror in
+ * cp-360-weakly-supervised-saliency_b200/ does exactly that.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch / CUDA types in signatures. `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).
+ *   - pointers named *_dev are device pointers, *_host are host pointers; the library never
+ *     allocates or frees caller memory and keeps no reference after the call returns.
+ *   - every call returns a cp360_status (0 = ok). Kernels are launched asynchronously on
+ *     `stream`; launch errors are reported, execution errors surface at the caller's next sync.
+ *   - thread-safe for distinct streams; no global mutable state except a thread-local
+ *     last-error string.
+ *   - there is NO CPU fallback: without a CUDA device the *_fwd/_bwd calls return
+ *     CP360_ERR_CUDA. The *_build_* calls are host-only (map construction, once per
+ *     resolution) and work anywhere.
+ *
+ * Face order everywhere: 0=Back 1=Down 2=Front 3=Left 4=Right 5=Top (cube_pad.py:49).
+ */
+#ifndef CP360_H_
+#define CP360_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CP360_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define CP360_API __attribute__((visibility("default")))
+#else
+#define CP360_API
+#endif
+
+typedef enum cp360_status {
+  CP360_OK = 0,
+  CP360_ERR_BAD_ARG = 1,      /* null pointer, negative size, unsupported elem size ...        */
+  CP360_ERR_GROUP = 2,        /* batch is not a multiple of 6 ("CubePad size mismatch!",       */
+                              /*   cube_pad.py:33-35 prints and exit()s; here: error code)     */
+  CP360_ERR_SHAPE = 3,        /* H != W, pad > H, Hin*2 != Win (equi_to_cube.py:15 assert) ... */
+  CP360_ERR_RANGE = 4,        /* map value outside the representable / interpolation range     */
+  CP360_ERR_CUDA = 5,         /* CUDA runtime / launch failure; see cp360_last_error()         */
+  CP360_ERR_ALIGN = 6         /* pointer not aligned to the element size                       */
+} cp360_status;
+
+CP360_API int cp360_version(void);
+CP360_API const char* cp360_status_string(int status);
+/* Thread-local, human readable detail of the last non-OK status on this thread ("" if none). */
+CP360_API const char* cp360_last_error(void);
+/* Number of kernels launched by this library since load (all threads); for bench accounting. */
+CP360_API uint64_t cp360_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * CubePad — model/cube_pad.py:23-216
+ * ---------------------------------------------------------------------------------------- */
+
+/* Host: output extent. Replaces the implicit shape arithmetic of cube_pad.py:179-215. */
+CP360_API int cp360_cubepad_out_shape(int H, int W, int pl, int pr, int pt, int pd, int* Ho, int* Wo);
+
+/* Host: the integer index map the kernels implement, as a table.
+ * map_host[6*Ho*Wo] (int32): for output pixel (face f, oy, ox) the flat index
+ * (src_face*H*W + src_row*W + src_col) into one channel's [6,H,W] cube.
+ * This is the closed form of cube_pad.py:106-215 (plates :114-162, corners :165-176). */
+CP360_API int cp360_cubepad_build_map(int H, int W, int pl, int pr, int pt, int pd, int32_t* map_host);
+
+/* Device: y[6N,C,Ho,Wo] = CubePad(x[6N,C,H,W]); contiguous NCHW, any element size in
+ * {1,2,4,8,16} bytes (pure data movement). n_faces = 6N must be a multiple of 6.
+ * Replaces CubePad.forward, cube_pad.py:28-42 (+ CubePadding.forward :95-216).
+ * Pad order is the reference's: l, r, t, d. */
+CP360_API int cp360_cubepad_fwd(const void* x_dev, void* y_dev, int64_t n_faces, int64_t C, int H, int W,
+                      int pl, int pr, int pt, int pd, int elem_bytes, void* stream);
+
+/* Same, with the kernel forced (tests / benchmarks): 0 auto, 1 generic gather, 2 band kernel with
+ * streaming stores, 3 band kernel with TMA bulk stores, 4 cube-tile kernel (all six faces of a
+ * channel group staged in shared memory). Non-applicable choices return CP360_ERR_SHAPE/ALIGN. */
+CP360_API int cp360_cubepad_fwd_algo(const void* x_dev, void* y_dev, int64_t n_faces, int64_t C, int H, int W,
+                           int pl, int pr, int pt, int pd, int elem_bytes, int algo, void* stream);
+
+/* Device, fp32: gx[6N,C,H,W] = dCubePad^T(gy[6N,C,Ho,Wo]) — every input pixel receives the sum
+ * of the gradients of all output pixels that copied it (what autograd derives from the
+ * cat/index_select/repeat chain; needed by temporal_model/train_temporal.py:167-170). */
+CP360_API int cp360_cubepad_bwd_f32(const float* gy_dev, float* gx_dev, int64_t n_faces, int64_t C, int H,
+                          int W, int pl, int pr, int pt, int pd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Equi2Cube — utils/equi_to_cube.py:11-129
+ * ---------------------------------------------------------------------------------------- */
+
+/* Host: sampling map for Hin x Win (Win == 2*Hin) -> 6 faces of w x w, vertical fov in degrees.
+ * Replaces Equi2Cube.__init__, equi_to_cube.py:12-110 (float64, table-lookup inverse trig) and
+ * the float32 cast + cv2 fixed-point conversion of :122-125 / cv2.remap.
+ * Outputs (any may be NULL):
+ *   packed_host[6*w*w] uint32  x0<<20 | y0<<10 | fx<<5 | fy  (x0 = sx>>5, fx = sx&31, ...)
+ *   sx_host, sy_host[6*w*w] int32   cvRound(float32(inX)*32), cvRound(float32(inY)*32)
+ *   inx_host, iny_host[6*w*w] double  the reference's self.inXs / self.inYs (1-based coords)
+ * Requires Win <= 2047 and Hin <= 1023 for the packed form (CP360_ERR_RANGE otherwise). */
+CP360_API int cp360_e2c_build_map(int w, int Hin, int Win, double vfov_deg, uint32_t* packed_host,
+                        int32_t* sx_host, int32_t* sy_host, double* inx_host, double* iny_host);
+
+#define CP360_LAYOUT_NCHW 0 /* faces[(b*6+f), c, y, x]   — what the cubic ResNet consumes        */
+#define CP360_LAYOUT_NHWC 1 /* faces[(b*6+f), y, x, c]   — the reference's dict of w x w x C     */
+
+/* Device, fp32: bilinear resampling with cv2.remap(INTER_LINEAR) fixed-point semantics
+ * (1/32-pixel weights, fp32, no FMA, BORDER_CONSTANT 0).
+ * frames_dev [B,Hin,Win,C] channel-contiguous; faces_dev [6B,...] in `out_layout`.
+ * If mean_host/std_host are non-NULL (C floats each) the per-channel normalisation
+ * (v - mean[c]) / std[c] of utils/utils.py:28-33 (im_norm, dataset_feat_extractor.py:148-151)
+ * is fused into the store.
+ * Replaces Equi2Cube.to_cube, equi_to_cube.py:112-129. */
+CP360_API int cp360_e2c_fwd(const float* frames_dev, const uint32_t* packed_dev, float* faces_dev,
+                  int64_t B, int Hin, int Win, int C, int w, int out_layout,
+                  const float* mean_host, const float* std_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cube2Equi — utils/cube_to_equi.py:11-66
+ * ---------------------------------------------------------------------------------------- */
+
+/* Host: replaces Cube2Equi.__init__, cube_to_equi.py:12-35 (+ sph_utils.py:53-153).
+ *   face_host[2w*4w] int8 (0..5), coord_host[2w*4w*2] double (x,y in face pixels). */
+CP360_API int cp360_c2e_build_map(int w, int8_t* face_host, double* coord_host);
+
+/* Host: the fp32 sampling plan to_equi_nn implies (cube_to_equi.py:58-64 + grid_sample):
+ *   M = max(float32(coord)); gn = (g - M/2)/(M/2); unnormalise (align_corners 0/1), floor,
+ *   four bilinear weights in torch's order nw, ne, sw, se — all in fp32.
+ *   tap_host[2w*4w] uint32: face<<28 | (y0+1)<<14 | (x0+1)   (x0,y0 in [-1, w-1])
+ *   wts_host[2w*4w*4] float.  M_out: the data-dependent normaliser (may be NULL). */
+CP360_API int cp360_c2e_build_plan(int w, int align_corners, uint32_t* tap_host, float* wts_host,
+                         float* M_out);
+
+/* Device, fp32: equi[B,C,2w,4w] from cube[6B,C,w,w]; out-of-face taps contribute 0
+ * (padding_mode='zeros'). Replaces Cube2Equi.to_equi_nn, cube_to_equi.py:37-66. */
+CP360_API int cp360_c2e_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
+                  float* equi_dev, int64_t B, int64_t C, int w, void* stream);
+
+/* Device, fp32: sal[B,2w,4w] = max over channels of the above, without materialising it
+ * (test_temporal.py:82-84, train_temporal.py:105-106, dataset_feat_extractor.py:174-175).
+ * NaNs are ignored by the max (torch.max would propagate them). */
+CP360_API int cp360_c2e_max_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
+                      float* sal_dev, int64_t B, int64_t C, int w, void* stream);
+
+/* Device, fp32: gcube[6B,C,w,w] = d(c2e)^T(gequi[B,C,2w,4w]) (bilinear scatter-add). */
+CP360_API int cp360_c2e_bwd(const float* gequi_dev, const uint32_t* tap_dev, const float* wts_dev,
+                  float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CP360_H_ */

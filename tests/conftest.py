@@ -25,3 +25,15 @@ def golden_meta():
 @pytest.fixture(scope="session")
 def golden_small():
     return np.load(os.path.join(GOLDEN_DIR, "golden_small.npz"))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The C-ABI library must exist for every test; build it here if nvcc is available."""
+    import cp360_b200
+    import shutil
+    if not os.path.exists(cp360_b200.LIB_PATH):
+        if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+            pytest.fail("libcp360.so missing and nvcc not available")
+        cp360_b200.build_library()
+    return cp360_b200.LIB_PATH

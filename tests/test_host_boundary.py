@@ -1,0 +1,130 @@
+"""CPU: the C-ABI boundary and the host map builders (no kernel launches).
+
+ * libcp360.so loads and exports every symbol include/cp360.h declares
+ * host-built integer maps == oracle == golden fixtures (bit-exact)
+ * error behaviour mirrors the reference's (size mismatch, 2:1 assert, square faces)
+"""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cp360_b200
+from cp360_b200 import _lib
+from oracle import c2e as oc2e
+from oracle import cubepad as ocp
+from oracle import e2c as oe2c
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "cp360.h")).read()
+    declared = set(re.findall(r"CP360_API\s+[\w\s\*]+?\b(cp360_\w+)\s*\(", hdr))
+    assert len(declared) >= 16
+    handle = ctypes.CDLL(cp360_b200.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), "libcp360.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert _lib.lib().cp360_version() == 100
+
+
+def test_cubepad_map_matches_oracle_and_golden(golden_meta, golden_small):
+    for key, info in golden_meta["cubepad_maps"].items():
+        m = cp360_b200.cubepad_index_map(info["H"], info["H"], info["pad"])
+        assert m.dtype == np.int32 and list(m.shape) == info["shape"]
+        assert sha(m) == info["sha256"], key                    # == reference output on arange
+        if info["H"] <= 64:
+            np.testing.assert_array_equal(m, ocp.index_map(info["H"], info["H"], info["pad"]))
+
+
+@pytest.mark.parametrize("H,pad", [(1, 1), (2, 2), (3, [3, 0, 1, 2]), (10, [0, 0, 0, 0]), (11, 5),
+                                   (12, [5, 1, 2, 4]), (13, [1, 5, 4, 2])])
+def test_cubepad_map_more_shapes_vs_oracle(H, pad):
+    np.testing.assert_array_equal(cp360_b200.cubepad_index_map(H, H, pad), ocp.index_map(H, H, pad))
+
+
+def test_cubepad_errors():
+    lib = _lib.lib()
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    assert lib.cp360_cubepad_out_shape(4, 5, 1, 1, 1, 1, ctypes.byref(ho), ctypes.byref(wo)) == 3
+    assert lib.cp360_cubepad_out_shape(4, 4, 5, 1, 1, 1, ctypes.byref(ho), ctypes.byref(wo)) == 3
+    assert lib.cp360_cubepad_out_shape(4, 4, 1, 2, 3, 0, ctypes.byref(ho), ctypes.byref(wo)) == 0
+    assert (ho.value, wo.value) == (7, 7)
+    # batch not a multiple of 6: status 2 before any device is touched (cube_pad.py:33-35)
+    assert lib.cp360_cubepad_fwd(None, None, 5, 1, 4, 4, 1, 1, 1, 1, 4, None) == 2
+    assert b"size mismatch" in lib.cp360_last_error()
+    assert lib.cp360_cubepad_fwd(None, None, 6, 1, 4, 4, 1, 1, 1, 1, 3, None) == 1   # elem size
+    assert lib.cp360_cubepad_fwd(None, None, 0, 8, 4, 4, 1, 1, 1, 1, 4, None) == 0   # empty batch
+    with pytest.raises(ValueError, match="size mismatch"):
+        _lib.check(2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cp360_b200.CubePad(1)(torch.zeros(6, 1, 4, 4))                               # CPU tensor
+    with pytest.raises(RuntimeError):
+        cp360_b200.CubePad(1, use_gpu=False)
+    assert cp360_b200.get_pad_size(2) == (2, 2, 2, 2)
+    assert cp360_b200.get_pad_size([1, 2, 3, 0]) == (1, 2, 3, 0)
+    assert len(list(cp360_b200.CubePad(1).parameters())) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
+def test_no_cpu_fallback_without_device():
+    buf = np.zeros(6 * 36, np.float32)
+    rc = _lib.lib().cp360_cubepad_fwd(buf.ctypes.data, buf.ctypes.data, 6, 1, 4, 4, 1, 1, 1, 1, 4, None)
+    assert rc == 5 and b"no CPU fallback" in _lib.lib().cp360_last_error()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cp360_b200.Equi2Cube(8, np.zeros((32, 64, 3), np.float32)).to_cube(np.zeros((32, 64, 3), np.float32))
+
+
+def test_e2c_maps_bit_exact(golden_meta, golden_small):
+    for key, info in golden_meta["e2c"].items():
+        w, H, W = info["w"], info["H"], info["W"]
+        obj = cp360_b200.Equi2Cube(w, np.empty((H, W, 3), np.float32), vfov=info["vfov"])
+        assert sha(np.concatenate([obj.sx.reshape(-1), obj.sy.reshape(-1)])) == info["sxsy_sha256"], key
+        np.testing.assert_array_equal(obj.packed.reshape(6, w, w), oe2c.pack_map(obj.sx, obj.sy))
+        inx32 = np.stack(obj.inXs).astype(np.float32)
+        iny32 = np.stack(obj.inYs).astype(np.float32)
+        assert sha(np.concatenate([inx32.reshape(-1), iny32.reshape(-1)])) == info["in32_sha256"], key
+        if key + "_inX" in golden_small.files:
+            np.testing.assert_allclose(np.stack(obj.inXs), golden_small[key + "_inX"], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(np.stack(obj.inYs), golden_small[key + "_inY"], rtol=0, atol=1e-9)
+            assert len(obj.inXs) == 6 and obj.inXs[0].shape == (w * w,) and obj.inXs[0].dtype == np.float64
+
+
+def test_e2c_errors():
+    with pytest.raises(AssertionError):
+        cp360_b200.Equi2Cube(8, np.zeros((32, 60, 3), np.float32))          # equi_to_cube.py:15
+    lib = _lib.lib()
+    assert lib.cp360_e2c_build_map(8, 32, 60, 90.0, None, None, None, None, None) == 3
+    big = np.empty(6 * 4 * 4, np.uint32)
+    assert lib.cp360_e2c_build_map(4, 2048, 4096, 90.0, big.ctypes.data, None, None, None, None) == 4
+    assert lib.cp360_e2c_fwd(None, None, None, 1, 32, 60, 3, 8, 0, None, None, None) == 3
+
+
+def test_c2e_maps_bit_exact(golden_meta, golden_small):
+    for key, info in golden_meta["c2e"].items():
+        w = info["w"]
+        obj = cp360_b200.Cube2Equi(w)
+        assert obj.face_map.dtype == np.float64 and obj.face_map.shape == (2 * w, 4 * w)
+        assert obj.out_coord.shape == (2 * w, 4 * w, 2)
+        assert sha(obj.face_map.astype(np.int64))[:16] == info["face_sha256_16"], key
+        assert sha(obj.out_coord.astype(np.float32))[:16] == info["coord32_sha256_16"], key
+        assert obj.M == info["M"]
+        face, coord = oc2e.build_maps(w)
+        np.testing.assert_allclose(obj.out_coord, coord, rtol=0, atol=1e-12)
+        for ac in (False, True):
+            o = cp360_b200.Cube2Equi(w, align_corners=ac)
+            x0, y0, wts, M = oc2e.sample_plan(coord, w, ac)
+            np.testing.assert_array_equal(o.weights.reshape(2 * w, 4 * w, 4), wts)   # fp32 bit-exact
+            np.testing.assert_array_equal((o.taps & 0x3fff).astype(np.int32).reshape(2 * w, 4 * w) - 1, x0)
+            np.testing.assert_array_equal(((o.taps >> 14) & 0x3fff).astype(np.int32).reshape(2 * w, 4 * w) - 1, y0)
+            np.testing.assert_array_equal((o.taps >> 28).reshape(2 * w, 4 * w), face.astype(np.uint32))
+            assert o.M == M
