@@ -442,6 +442,13 @@ static int validate(const void* x, void* y, int64_t n_faces, int64_t C, int H, i
   return CP360_OK;
 }
 
+static int pick_algo(const CubePadGeom& g, int C, bool fast_ok) {
+  int k; size_t smem;
+  if (fast_ok && g.H <= 32 && cube_plan(g, C, &k, &smem)) return ALGO_CUBE;
+  if (fast_ok && band_ok(g) && g.H >= 24) return ALGO_BAND_BULK;
+  return ALGO_GENERIC;
+}
+
 }  // namespace cp360
 
 using namespace cp360;
@@ -472,6 +479,16 @@ int cp360_cubepad_build_map(int H, int W, int pl, int pr, int pt, int pd, int32_
   return CP360_OK;
 }
 
+int cp360_cubepad_pick_algo(int64_t C, int H, int W, int pl, int pr, int pt, int pd, int elem_bytes,
+                            int aligned16) {
+  CubePadGeom g;
+  if (!make_geom(H, W, pl, pr, pt, pd, &g) || C < 0 || C > 0x7fffffff) {
+    set_error("CubePad needs square faces and 0 <= pad <= H");
+    return -CP360_ERR_SHAPE;
+  }
+  return pick_algo(g, (int)C, elem_bytes == 4 && aligned16 != 0);
+}
+
 int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
                            int pr, int pt, int pd, int elem_bytes, int algo, void* stream) {
   CubePadGeom g;
@@ -489,12 +506,7 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
   const int64_t n_planes = n_faces * C;
   const bool fast_ok = elem_bytes == 4 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
 
-  if (algo == ALGO_AUTO) {
-    int k; size_t smem;
-    if (fast_ok && H <= 32 && cube_plan(g, (int)C, &k, &smem)) algo = ALGO_CUBE;
-    else if (fast_ok && band_ok(g) && H >= 24) algo = ALGO_BAND_BULK;
-    else algo = ALGO_GENERIC;
-  }
+  if (algo == ALGO_AUTO) algo = pick_algo(g, (int)C, fast_ok);
   switch (algo) {
     case ALGO_CUBE:
       CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "cube-tile kernel needs 4-byte elements, 16 B aligned");

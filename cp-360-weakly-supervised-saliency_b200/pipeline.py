@@ -1,0 +1,214 @@
+"""SphericalPipeline — the batched, frame-sharded chain the benchmark measures
+(BASELINE.json metric: frames/sec equi->cube->CubePad->cube->equi @1920x960).
+
+One *step* processes B frames that are independent of each other, in the order
+the reference's static-inference loop touches the three operators
+(static_model/dataset_feat_extractor.py:145,161,174 + model/resnet_cubic.py:165-170,92):
+
+  K1  Equi2Cube            frames[B,Hin,Win,3]  -> faces[6B,3,w,w]                (e2c.cu)
+  K2  CubePad x 18         the 18 CubePad sites of one cubic ResNet-50 forward; site 0 pads the
+                           faces K1 just produced, sites 1..17 pad device-resident feature tensors
+                           of the exact site shapes (the convolutions between them are cuDNN's
+                           business and out of scope, so the features are synthetic stand-ins)
+  K2  CubePad(1) 2048-ch   [6B,2048,w/32,w/32]  -> [6B,2048,w/32+2,w/32+2]  (BASELINE's 2048-channel
+                           CubePad; the ConvLSTM-side site, model/clstm.py:58-64)
+  K3m Cube2Equi + max      cam[6B,1000,w/32,w/32] -> sal[B,2w/32,4w/32]            (c2e.cu)
+
+All launches go through the C-ABI (include/cp360.h) on the caller's current stream; buffers are
+allocated once per (B, device) and reused; the step can be captured in a CUDA graph.
+Frames are partitioned over ranks in contiguous blocks; no collective is needed inside a step —
+``gather_maps`` is the single final exchange.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .cube_to_equi import Cube2Equi
+from .equi_to_cube import Equi2Cube
+
+
+def resnet50_cubepad_sites(cube):
+    """(C, H, pad) of the 18 CubePad calls of one cubic ResNet-50 forward at face width `cube`
+    (model/resnet_cubic.py:71,92,116-117,165,169)."""
+    d = int(cube)
+    return ([(3, d, 3), (64, d // 2, 1)] + [(64, d // 4, 1)] * 3 + [(128, d // 4, 1)] +
+            [(128, d // 8, 1)] * 3 + [(256, d // 8, 1)] + [(256, d // 16, 1)] * 5 +
+            [(512, d // 16, 1)] + [(512, d // 32, 1)] * 2)
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block partition of n_items over `world` ranks -> (start, stop) of `rank`."""
+    base, rem = divmod(int(n_items), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_maps(local_maps, n_total, group=None):
+    """The one collective of the path: every rank contributes its [n_local,h,w] saliency maps,
+    every rank gets the [n_total,h,w] stack in frame order (NCCL on GPU tensors, gloo on CPU)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_maps
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    n_max = max(b - a for a, b in sizes)
+    pad = torch.zeros((n_max,) + tuple(local_maps.shape[1:]), dtype=local_maps.dtype, device=local_maps.device)
+    pad[:local_maps.shape[0]] = local_maps
+    out = torch.empty((world * n_max,) + tuple(local_maps.shape[1:]), dtype=local_maps.dtype,
+                      device=local_maps.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * n_max:r * n_max + (b - a)] for r, (a, b) in enumerate(sizes)], 0)
+
+
+class SphericalPipeline:
+    def __init__(self, equi_h=960, equi_w=1920, cube=256, cam_channels=1000, feat_channels=2048,
+                 device=None, seed=1234):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SphericalPipeline needs a CUDA device (sm_100a); no CPU fallback")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.equi_h, self.equi_w, self.cube = int(equi_h), int(equi_w), int(cube)
+        self.feat_w = self.cube // 32
+        self.cam_channels, self.feat_channels = int(cam_channels), int(feat_channels)
+        self.e2c = Equi2Cube(self.cube, np.empty((self.equi_h, self.equi_w, 3), np.float32))
+        self.c2e = Cube2Equi(self.feat_w)
+        self.sites = resnet50_cubepad_sites(self.cube) + [(self.feat_channels, self.feat_w, 1)]
+        self.seed = seed
+        self.B = 0
+        self._lib = _lib.lib()
+
+    # ---------------------------------------------------------------- accounting
+    def e2c_bytes_per_frame(self):
+        """Algorithmic bytes of K1: unique input pixels touched * C * 4 + faces written."""
+        w = self.cube
+        p = self.e2c.packed.astype(np.int64)
+        x0, y0 = p >> 20, (p >> 10) & 1023
+        fx, fy = (p >> 5) & 31, p & 31
+        W = self.equi_w
+        touched = [y0 * W + x0, (y0 * W + x0 + 1)[fx > 0], ((y0 + 1) * W + x0)[fy > 0],
+                   ((y0 + 1) * W + x0 + 1)[(fx > 0) & (fy > 0)]]
+        n = np.unique(np.concatenate([t.reshape(-1) for t in touched])).size
+        return int(n) * 3 * 4 + 6 * w * w * 3 * 4
+
+    def cubepad_bytes_per_frame(self, site):
+        C, H, p = site
+        return 6 * C * (H * H + (H + 2 * p) * (H + 2 * p)) * 4
+
+    def c2e_max_bytes_per_frame(self):
+        w = self.feat_w
+        return 6 * self.cam_channels * w * w * 4 + 8 * w * w * 4
+
+    def bytes_per_frame(self):
+        return (self.e2c_bytes_per_frame() + sum(self.cubepad_bytes_per_frame(s) for s in self.sites) +
+                self.c2e_max_bytes_per_frame())
+
+    # ---------------------------------------------------------------- buffers
+    def allocate(self, B):
+        """Device buffers for B frames per step; synthetic resident features (seeded)."""
+        dev, w = self.device, self.cube
+        g = torch.Generator(device=dev).manual_seed(self.seed)
+        self.B = int(B)
+        n = 6 * self.B
+        self.faces = torch.empty((n, 3, w, w), dtype=torch.float32, device=dev)
+        self.site_in, self.site_out = [self.faces], []
+        for i, (C, H, p) in enumerate(self.sites):
+            if i > 0:
+                self.site_in.append(torch.randn((n, C, H, H), dtype=torch.float32, device=dev, generator=g))
+            self.site_out.append(torch.empty((n, C, H + 2 * p, H + 2 * p), dtype=torch.float32, device=dev))
+        fw = self.feat_w
+        self.cam = torch.randn((n, self.cam_channels, fw, fw), dtype=torch.float32, device=dev, generator=g)
+        self.sal = torch.empty((self.B, 2 * fw, 4 * fw), dtype=torch.float32, device=dev)
+        self._packed = self.e2c._map_on(dev)
+        self._taps, self._wts = self.c2e._plan_on(dev)
+        return self
+
+    def synthetic_frames(self, B, generator=None):
+        """U[0,1) fp32 frames [B,Hin,Win,3] on the device (Wild-360-shaped)."""
+        g = generator or torch.Generator(device=self.device).manual_seed(self.seed + 1)
+        return torch.rand((B, self.equi_h, self.equi_w, 3), dtype=torch.float32, device=self.device, generator=g)
+
+    # ---------------------------------------------------------------- the step
+    def launches_per_step(self):
+        return 1 + len(self.sites) + 2          # e2c, CubePads, -inf fill + c2e_max
+
+    def step(self, frames, on_launch=None):
+        """frames [B,Hin,Win,3] fp32 on self.device -> sal [B,2fw,4fw] (buffer reused each step).
+
+        on_launch(name, site_index): optional hook called before every C-ABI call and once after
+        the last (bench.py uses it to drop CUDA events between kernels)."""
+        if frames.shape[0] != self.B:
+            self.allocate(frames.shape[0])
+        lib, chk = self._lib, _lib.check
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        n = 6 * self.B
+        if on_launch:
+            on_launch("e2c", -1)
+        chk(lib.cp360_e2c_fwd(frames.data_ptr(), self._packed.data_ptr(), self.faces.data_ptr(), self.B,
+                              self.equi_h, self.equi_w, 3, self.cube, _lib.LAYOUT_NCHW, None, None, st))
+        for i, (C, H, p) in enumerate(self.sites):
+            if on_launch:
+                on_launch("cubepad", i)
+            chk(lib.cp360_cubepad_fwd(self.site_in[i].data_ptr(), self.site_out[i].data_ptr(), n, C, H, H,
+                                      p, p, p, p, 4, st))
+        if on_launch:
+            on_launch("c2e_max", -1)
+        chk(lib.cp360_c2e_max_fwd(self.cam.data_ptr(), self._taps.data_ptr(), self._wts.data_ptr(),
+                                  self.sal.data_ptr(), self.B, self.cam_channels, self.feat_w, st))
+        if on_launch:
+            on_launch("end", -1)
+        return self.sal
+
+    def capture(self, frames):
+        """Capture one step over `frames` (a fixed device buffer) in a CUDA graph; returns the
+        graph (call .replay()). The first eager step doubles as warm-up (function attributes)."""
+        self.step(frames)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(frames)
+        return graph
+
+    # ---------------------------------------------------------------- host-buffer entry point
+    def run_host(self, frames_host, out_host=None):
+        """End-to-end call with HOST buffers: frames_host [B,Hin,Win,3] fp32 (pinned for async
+        copies) -> saliency maps [B,2fw,4fw] on the host. H2D + chain + D2H on the current stream."""
+        frames = frames_host.to(self.device, non_blocking=True)
+        sal = self.step(frames)
+        if out_host is None:
+            return sal.cpu()
+        out_host.copy_(sal, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
+
+    def process_host(self, host_batches, out_host):
+        """Streamed end-to-end path: host_batches is a sequence of pinned [B,Hin,Win,3] fp32 host
+        tensors, out_host a pinned [len(host_batches),B,2fw,4fw] tensor. Uploads run on a copy
+        stream into two alternating device buffers while the previous batch computes; every
+        batch's maps are copied back to the host. Returns after everything has landed."""
+        dev = self.device
+        B = host_batches[0].shape[0]
+        if B != self.B:
+            self.allocate(B)
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] != B:
+            self._stage = [torch.empty((B, self.equi_h, self.equi_w, 3), dtype=torch.float32, device=dev)
+                           for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        compute = torch.cuda.current_stream(dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [None, None]
+        self._copy_stream.wait_stream(compute)
+        for i, hb in enumerate(host_batches):
+            k = i & 1
+            with torch.cuda.stream(self._copy_stream):
+                if freed[k] is not None:
+                    self._copy_stream.wait_event(freed[k])
+                self._stage[k].copy_(hb, non_blocking=True)
+                copied[k].record(self._copy_stream)
+            compute.wait_event(copied[k])
+            sal = self.step(self._stage[k])
+            freed[k] = torch.cuda.Event()
+            freed[k].record(compute)
+            out_host[i].copy_(sal, non_blocking=True)
+        compute.synchronize()
+        return out_host

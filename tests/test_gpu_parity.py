@@ -1,0 +1,367 @@
+"""GPU parity: the sm_100a kernels, called through the C-ABI (ctypes host mirror), against
+ * the numpy oracle on the same seeded inputs,
+ * the golden fixtures produced by executing the reference (tests/golden/make_golden.py),
+ * size-independent properties at BASELINE.json's full sizes.
+
+Bars (BASELINE.json north_star): CubePad output and integer maps BIT-EXACT; e2c faces bit-exact
+against cv2.remap's fixed-point arithmetic (tolerance 0, stricter than the 1e-5 asked);
+c2e maps max-abs <= 1e-5 (fp32).
+"""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import cp360_b200
+from cp360_b200 import _lib
+from oracle import c2e as oc2e
+from oracle import cubepad as ocp
+from oracle import e2c as oe2c
+
+pytestmark = pytest.mark.gpu
+
+C2E_TOL = 1e-5     # north_star: back-projected float maps within max-abs 1e-5 (fp32)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def gather_reference(x, imap):
+    """torch fancy-index application of a host index map (independent of the kernels)."""
+    n6, C, H, W = x.shape
+    _, Ho, Wo = imap.shape
+    g = x.reshape(n6 // 6, 6, C, H * W).permute(0, 2, 1, 3).reshape(n6 // 6, C, 6 * H * W)
+    idx = torch.from_numpy(imap.reshape(-1).astype(np.int64)).to(x.device)
+    out = g.index_select(2, idx).reshape(n6 // 6, C, 6, Ho, Wo).permute(0, 2, 1, 3, 4)
+    return out.reshape(n6, C, Ho, Wo).contiguous()
+
+
+ALGOS = [_lib.ALGO_AUTO, _lib.ALGO_GENERIC, _lib.ALGO_BAND_STG, _lib.ALGO_BAND_BULK, _lib.ALGO_CUBE]
+
+
+# ------------------------------------------------------------------------------------------
+# CubePad
+# ------------------------------------------------------------------------------------------
+def test_cubepad_kat_hashes(dev, golden_meta):
+    """KAT table of SURVEY.md §8c: x = arange, output hashed by the reference run."""
+    for kat in golden_meta["cubepad_kat"]:
+        x = torch.arange(int(np.prod(kat["shape"])), dtype=torch.float32, device=dev).reshape(kat["shape"])
+        y = cp360_b200.CubePad(kat["pad"])(x)
+        assert list(y.shape) == kat["out_shape"]
+        assert sha(y.cpu().numpy()) == kat["sha256"], kat
+
+
+def test_cubepad_random_multigroup_golden(dev, golden_meta, golden_small):
+    info = golden_meta["cubepad_rand"]
+    x = np.random.default_rng(info["seed"]).standard_normal(info["shape"]).astype(np.float32)
+    y = cp360_b200.CubePad(info["pad"])(torch.from_numpy(x).to(dev))
+    np.testing.assert_array_equal(y.cpu().numpy(), golden_small["cubepad_rand_12x5x6x6_p2-1-1-3"])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("shape,pad", [
+    ((6, 4, 4, 4), 1), ((12, 8, 7, 7), 1), ((6, 16, 8, 8), 1), ((18, 12, 14, 14), 1), ((6, 8, 16, 16), 1),
+    ((6, 4, 28, 28), 1), ((12, 4, 32, 32), 1), ((6, 5, 56, 56), 1), ((6, 3, 64, 64), 1), ((6, 2, 112, 112), 1),
+    ((6, 2, 128, 128), 1), ((6, 3, 224, 224), 3), ((12, 3, 256, 256), 3), ((6, 2, 256, 256), 2),
+    ((6, 4, 6, 6), [1, 2, 3, 0]), ((6, 4, 8, 8), [2, 1, 1, 3]), ((6, 8, 9, 9), [4, 2, 3, 5]),
+    ((6, 4, 5, 5), [0, 0, 0, 0]), ((6, 3, 7, 7), 1), ((6, 1, 1, 1), 1), ((6, 4, 2, 2), 2),
+    ((6, 4, 40, 40), [3, 3, 1, 1]), ((6, 2, 30, 30), [0, 2, 1, 0]),
+])
+def test_cubepad_vs_oracle(dev, shape, pad, algo):
+    rng = np.random.default_rng(zlib.crc32(repr((shape, pad)).encode()))
+    x = rng.standard_normal(shape).astype(np.float32)
+    want = ocp.cubepad(x, pad)
+    xt = torch.from_numpy(x).to(dev)
+    try:
+        y = cp360_b200.cubepad_forward(xt, cp360_b200.get_pad_size(pad), algo=algo)
+    except _lib.CP360Error as e:
+        if algo in (_lib.ALGO_AUTO, _lib.ALGO_GENERIC):
+            raise
+        pytest.skip("algo %d does not apply: %s" % (algo, e))
+    np.testing.assert_array_equal(y.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float16, torch.bfloat16, torch.float64, torch.int64,
+                                   torch.complex128])
+def test_cubepad_any_dtype(dev, dtype):
+    """Pure data movement: every element size 1..16 bytes is bit-exact."""
+    x = torch.randn(12, 6, 10, 10, device=dev)
+    imap = ocp.index_map(10, 10, [1, 2, 2, 1])
+    if dtype == torch.complex128:
+        x = torch.complex(x.double(), -x.double())
+        y = cp360_b200.CubePad([1, 2, 2, 1])(x)
+        re = gather_reference(x.real.contiguous(), imap)
+        im = gather_reference(x.imag.contiguous(), imap)
+        assert torch.equal(y.real, re) and torch.equal(y.imag, im)
+    else:
+        x = (x.abs() * 50).to(dtype)
+        y = cp360_b200.CubePad([1, 2, 2, 1])(x)
+        assert y.dtype == dtype and torch.equal(y, gather_reference(x, imap))
+
+
+def resnet50_sites(cube):
+    """(C, H, pad) of the 18 CubePad calls of one ResNet-50 forward."""
+    d = cube
+    return ([(3, d, 3), (64, d // 2, 1)] + [(64, d // 4, 1)] * 3 + [(128, d // 4, 1)] + [(128, d // 8, 1)] * 3 +
+            [(256, d // 8, 1)] + [(256, d // 16, 1)] * 5 + [(512, d // 16, 1)] + [(512, d // 32, 1)] * 2)
+
+
+@pytest.mark.parametrize("cube", [224, 256])
+def test_cubepad_resnet50_sites_full_size(dev, cube, golden_meta):
+    """All 18 ResNet-50 site shapes, 2 frames, against a torch gather through the host index map
+    (itself hash-pinned to the reference in test_host_boundary / golden.json)."""
+    seen = set()
+    for C, H, p in resnet50_sites(cube):
+        if (C, H, p) in seen:
+            continue
+        seen.add((C, H, p))
+        x = torch.randn(12, C, H, H, device=dev)
+        y = cp360_b200.CubePad(p)(x)
+        imap = cp360_b200.cubepad_index_map(H, H, p)
+        key = "cubepad_map_H%d_p%d" % (H, p)
+        if key in golden_meta["cubepad_maps"]:
+            assert sha(imap) == golden_meta["cubepad_maps"][key]["sha256"]
+        assert torch.equal(y, gather_reference(x, imap)), (C, H, p)
+
+
+def test_cubepad_selftest_and_clstm_shapes(dev):
+    """README self-test [12,64,256,256] p2 (cube_pad.py:256-261) and the ConvLSTM / BASELINE
+    2048-channel sites."""
+    for shape, p in [((12, 64, 256, 256), 2), ((6, 2000, 7, 7), 1), ((6, 4000, 7, 7), 1),
+                     ((96, 2048, 8, 8), 1), ((6, 4096, 8, 8), 1), ((6, 8192, 8, 8), 1)]:
+        x = torch.randn(shape, device=dev)
+        y = cp360_b200.CubePad(p)(x)
+        assert tuple(y.shape) == (shape[0], shape[1], shape[2] + 2 * p, shape[3] + 2 * p)
+        imap = cp360_b200.cubepad_index_map(shape[2], shape[3], p)
+        assert torch.equal(y, gather_reference(x, imap)), shape
+        # interior is the input, untouched
+        assert torch.equal(y[:, :, p:-p, p:-p], x)
+
+
+def test_cubepad_errors_and_edge_cases(dev):
+    with pytest.raises(ValueError, match="size mismatch"):
+        cp360_b200.CubePad(1)(torch.zeros(5, 2, 4, 4, device=dev))
+    with pytest.raises(_lib.CP360Error):
+        cp360_b200.CubePad(1)(torch.zeros(6, 2, 4, 5, device=dev))       # H != W
+    with pytest.raises(_lib.CP360Error):
+        cp360_b200.CubePad(5)(torch.zeros(6, 2, 4, 4, device=dev))       # pad > H
+    y = cp360_b200.CubePad(1)(torch.zeros(0, 3, 4, 4, device=dev))        # empty batch
+    assert tuple(y.shape) == (0, 3, 6, 6)
+    y = cp360_b200.CubePad(1)(torch.zeros(6, 0, 4, 4, device=dev))        # no channels
+    assert tuple(y.shape) == (6, 0, 6, 6)
+    # non-contiguous input and a misaligned (4 B but not 16 B aligned) view
+    base = torch.randn(6, 4, 8, 9, device=dev)
+    x = base[:, :, :, :8]
+    assert torch.equal(cp360_b200.CubePad(1)(x), gather_reference(x.contiguous(), ocp.index_map(8, 8, 1)))
+    flat = torch.randn(6 * 4 * 64 + 1, device=dev)[1:]
+    x = flat.view(6, 4, 8, 8)
+    assert x.data_ptr() % 16 != 0
+    assert torch.equal(cp360_b200.CubePad(1)(x), gather_reference(x, ocp.index_map(8, 8, 1)))
+
+
+def test_cubepad_backward_matches_autograd(dev):
+    """Backward = transpose of the gather (train_temporal.py:167-170 back-propagates through it)."""
+    for shape, pad in [((6, 3, 7, 7), 1), ((12, 4, 8, 8), [2, 1, 1, 3]), ((6, 2, 32, 32), 3)]:
+        x = torch.randn(shape, device=dev, dtype=torch.float32, requires_grad=True)
+        y = cp360_b200.CubePad(pad)(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        x2 = x.detach().clone().requires_grad_(True)
+        gather_reference(x2, ocp.index_map(shape[2], shape[3], pad)).backward(gy)
+        torch.testing.assert_close(x.grad, x2.grad, rtol=0, atol=1e-5)
+
+
+def test_cubepad_is_stream_ordered(dev):
+    s = torch.cuda.Stream(device=dev)
+    x = torch.randn(6, 64, 32, 32, device=dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        y = cp360_b200.CubePad(1)(x)
+    s.synchronize()
+    assert torch.equal(y, gather_reference(x, ocp.index_map(32, 32, 1)))
+
+
+# ------------------------------------------------------------------------------------------
+# Equi2Cube
+# ------------------------------------------------------------------------------------------
+def test_e2c_faces_golden_bit_exact(dev, golden_meta, golden_small):
+    """faces == cv2.remap(INTER_LINEAR) fp32 output of the reference, bit for bit (sha + arrays)."""
+    for key, info in golden_meta["e2c"].items():
+        w, H, W = info["w"], info["H"], info["W"]
+        img = np.random.default_rng(info["seed"]).random((H, W, 3), dtype=np.float32)
+        e2c = cp360_b200.Equi2Cube(w, img, vfov=info["vfov"])
+        faces = e2c.to_cube(img)                                       # reference API: dict of [w,w,3]
+        assert sorted(faces) == list(range(6)) and faces[0].shape == (w, w, 3) and faces[0].dtype == np.float32
+        stack = np.stack([faces[i] for i in range(6)])
+        assert sha(stack) == info["faces_sha256"], key
+        if key + "_faces" in golden_small.files:
+            np.testing.assert_array_equal(stack, golden_small[key + "_faces"])
+        # NCHW tensor entry point carries the same numbers
+        t = e2c.to_cube_tensor(torch.from_numpy(img).to(dev))
+        np.testing.assert_array_equal(t.permute(0, 2, 3, 1).cpu().numpy(), stack)
+
+
+@pytest.mark.parametrize("C", [1, 2, 3, 4, 7])
+def test_e2c_vs_oracle_channels_and_batch(dev, C):
+    w, H, W, B = 24, 96, 192, 3
+    rng = np.random.default_rng(77 + C)
+    frames = rng.random((B, H, W, C), dtype=np.float32)
+    e2c = cp360_b200.Equi2Cube(w, frames[0])
+    sx, sy = oe2c.fixed_maps(w, H, W)
+    np.testing.assert_array_equal(e2c.sx, sx)
+    out = e2c.to_cube_tensor(torch.from_numpy(frames).to(dev), layout="NHWC").cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(out[6 * b:6 * b + 6], oe2c.to_cube(frames[b], sx, sy))
+
+
+def test_e2c_fused_norm(dev):
+    """im_norm fused into the store (utils/utils.py:28-33): (v - mean) / std per channel."""
+    w, H, W = 32, 128, 256
+    img = np.random.default_rng(5).random((H, W, 3), dtype=np.float32)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    e2c = cp360_b200.Equi2Cube(w, img)
+    plain = e2c.to_cube_tensor(torch.from_numpy(img).to(dev))
+    fused = e2c.to_cube_tensor(torch.from_numpy(img).to(dev), mean=mean, std=std)
+    want = (plain.cpu().numpy() - np.float32(mean).reshape(1, 3, 1, 1)) / np.float32(std).reshape(1, 3, 1, 1)
+    np.testing.assert_array_equal(fused.cpu().numpy(), want.astype(np.float32))
+
+
+def test_e2c_float64_input_follows_dtype(dev):
+    img = np.random.default_rng(9).random((64, 128, 3))            # float64 like dataset_feat_extractor.py:142
+    faces = cp360_b200.Equi2Cube(16, img).to_cube(img)
+    assert faces[2].dtype == np.float64 and faces[2].shape == (16, 16, 3)
+    sx, sy = oe2c.fixed_maps(16, 64, 128)
+    np.testing.assert_allclose(np.stack([faces[i] for i in range(6)]),
+                               oe2c.to_cube(img.astype(np.float32), sx, sy), rtol=0, atol=1e-7)
+
+
+def test_e2c_full_size_properties(dev):
+    """1920x960 -> 256: constant frame -> constant faces (weights sum to 1 exactly in fp32 for
+    k/32 fractions), linearity in the frame, and batch entries independent."""
+    H, W, w = 960, 1920, 256
+    e2c = cp360_b200.Equi2Cube(w, np.empty((H, W, 3), np.float32))
+    const = torch.full((1, H, W, 3), 0.75, device=dev)
+    assert torch.equal(e2c.to_cube_tensor(const), torch.full((6, 3, w, w), 0.75, device=dev))
+    g = torch.Generator(device=dev).manual_seed(3)
+    a = torch.rand(2, H, W, 3, device=dev, generator=g)
+    fa = e2c.to_cube_tensor(a)
+    f0 = e2c.to_cube_tensor(a[0])
+    f1 = e2c.to_cube_tensor(a[1])
+    assert torch.equal(fa[:6], f0) and torch.equal(fa[6:], f1)
+    f2 = e2c.to_cube_tensor(a[0] * 2.0)                  # scaling by 2 is exact in fp32
+    assert torch.equal(f2, f0 * 2.0)
+
+
+# ------------------------------------------------------------------------------------------
+# Cube2Equi
+# ------------------------------------------------------------------------------------------
+def test_c2e_golden(dev, golden_meta, golden_small):
+    for key, info in golden_meta["c2e"].items():
+        w, C = info["w"], info["C"]
+        cube = np.random.default_rng(info["seed"]).standard_normal((6, C, w, w)).astype(np.float32)
+        c2e = cp360_b200.Cube2Equi(w)
+        out = c2e.to_equi_nn(torch.from_numpy(cube).to(dev))
+        assert tuple(out.shape) == (1, C, 2 * w, 4 * w) and out.is_cuda
+        out = out.cpu().numpy()
+        if key + "_out" in golden_small.files:
+            assert np.abs(out - golden_small[key + "_out"]).max() <= C2E_TOL, key
+        else:
+            assert np.abs(out[:, :, ::7, ::11] - golden_small[key + "_out_probe"]).max() <= C2E_TOL, key
+        assert abs(float(out.astype(np.float64).sum()) - info["out_sum"]) < 1e-2
+
+
+@pytest.mark.parametrize("w,C,B", [(7, 1000, 1), (8, 1000, 2), (8, 2048, 3), (7, 10, 2), (14, 6, 1), (16, 64, 2),
+                                   (5, 3, 1), (20, 4, 2), (64, 3, 1), (8, 7, 1)])
+@pytest.mark.parametrize("align", [False, True])
+def test_c2e_vs_oracle(dev, w, C, B, align):
+    rng = np.random.default_rng(w * 1000 + C)
+    cube = rng.standard_normal((6 * B, C, w, w)).astype(np.float32)
+    face, coord = oc2e.build_maps(w)
+    c2e = cp360_b200.Cube2Equi(w, align_corners=align)
+    t = torch.from_numpy(cube).to(dev)
+    out = c2e.to_equi_nn(t).cpu().numpy()
+    sal = c2e.to_equi_max(t).cpu().numpy()
+    for b in range(B):
+        want = oc2e.to_equi(cube[6 * b:6 * b + 6], face, coord, align)
+        assert np.abs(out[b] - want[0]).max() <= C2E_TOL
+        assert np.abs(sal[b] - want[0].max(axis=0)).max() <= C2E_TOL
+
+
+def test_c2e_numpy_input_and_errors(dev):
+    c2e = cp360_b200.Cube2Equi(7)
+    cube = np.random.default_rng(1).standard_normal((6, 9, 7, 7)).astype(np.float32)
+    out = c2e.to_equi_nn(cube)                       # dataset_feat_extractor.py:174 passes ndarray
+    assert out.is_cuda and tuple(out.shape) == (1, 9, 14, 28)
+    with pytest.raises(ValueError):
+        c2e.to_equi_nn(torch.zeros(5, 3, 7, 7, device=dev))
+    with pytest.raises(ValueError):
+        c2e.to_equi_nn(torch.zeros(6, 3, 8, 8, device=dev))
+    with pytest.raises(RuntimeError):
+        c2e.to_equi_nn(torch.zeros(6, 3, 7, 7))
+
+
+def test_c2e_vs_torch_grid_sample(dev):
+    """The reference's own formulation (cube_to_equi.py:58-65) executed with torch CUDA ops."""
+    import torch.nn.functional as F
+    for w, C in [(8, 64), (16, 8), (7, 33)]:
+        c2e = cp360_b200.Cube2Equi(w)
+        x = torch.randn(6, C, w, w, device=dev)
+        g = torch.from_numpy(c2e.out_coord.astype(np.float32)).to(dev)
+        fm = torch.from_numpy(c2e.face_map.astype(np.int64)).to(dev)
+        M = g.max()
+        gn = ((g - M / 2) / (M / 2))[None]
+        want = torch.zeros(1, C, 2 * w, 4 * w, device=dev)
+        for f in range(6):
+            s = F.grid_sample(x[f:f + 1], gn, mode="bilinear", padding_mode="zeros", align_corners=False)
+            m = (fm == f)[None, None].expand_as(want)
+            want[m] = s[m]
+        got = c2e.to_equi_nn(x)
+        assert (got - want).abs().max().item() <= C2E_TOL
+        assert (c2e.to_equi_max(x) - want.max(1)[0]).abs().max().item() <= C2E_TOL
+
+
+def test_c2e_backward_matches_autograd(dev):
+    for w, C in [(7, 5), (8, 16), (20, 3)]:
+        c2e = cp360_b200.Cube2Equi(w)
+        x = torch.randn(6, C, w, w, device=dev, requires_grad=True)
+        y = c2e.to_equi_nn(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        # dense transpose built from the plan
+        taps = torch.from_numpy(c2e.taps.astype(np.int64)).to(dev)
+        wts = torch.from_numpy(c2e.weights).to(dev)
+        face, y0, x0 = taps >> 28, ((taps >> 14) & 0x3fff) - 1, (taps & 0x3fff) - 1
+        want = torch.zeros(6, C, w, w, device=dev, dtype=torch.float64)
+        gyf = gy[0].reshape(C, -1).double()
+        for k, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+            yy, xx = y0 + dy, x0 + dx
+            ok = (yy >= 0) & (yy < w) & (xx >= 0) & (xx < w)
+            idx = (face * w * w + yy.clamp(0, w - 1) * w + xx.clamp(0, w - 1))[ok]
+            contrib = (gyf * wts[:, k].double())[:, ok]
+            flat = want.permute(1, 0, 2, 3).reshape(C, -1)
+            flat.index_add_(1, idx, contrib)
+            want = flat.reshape(C, 6, w, w).permute(1, 0, 2, 3).contiguous()
+        torch.testing.assert_close(x.grad.double(), want, rtol=0, atol=1e-4)
+
+
+def test_c2e_full_size_properties(dev):
+    """BASELINE shapes: [96,2048,8,8] -> max map; fused max == max of the materialised map,
+    and linearity of the un-fused op (x -> 2x exact in fp32)."""
+    c2e = cp360_b200.Cube2Equi(8)
+    x = torch.randn(96, 2048, 8, 8, device=dev)
+    full = c2e.to_equi_nn(x)
+    assert tuple(full.shape) == (16, 2048, 16, 32)
+    assert torch.equal(c2e.to_equi_max(x), full.max(1)[0])
+    assert torch.equal(c2e.to_equi_nn(x * 2.0), full * 2.0)
+    c2e7 = cp360_b200.Cube2Equi(7)
+    x7 = torch.randn(6, 1000, 7, 7, device=dev)
+    assert torch.equal(c2e7.to_equi_max(x7), c2e7.to_equi_nn(x7).max(1)[0])

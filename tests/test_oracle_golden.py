@@ -105,3 +105,43 @@ def test_c2e_maps_and_output(golden_meta, golden_small):
             assert np.abs(out - ref).max() <= 4e-6, key   # tolerance: CPU grid_sample vs restatement
         else:
             assert np.abs(out[:, :, ::7, ::11] - golden_small[key + "_out_probe"]).max() <= 4e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle.ref_port — the library-call port timed as bench.py's CPU baseline
+# ---------------------------------------------------------------------------------------------
+def test_ref_port_cubepad(golden_meta, golden_small):
+    import torch
+    from oracle import ref_port
+    for key, info in golden_meta["cubepad_maps"].items():
+        H = info["H"]
+        if H > 64:
+            continue
+        x = torch.arange(6 * H * H, dtype=torch.float64).reshape(6, 1, H, H)
+        y = ref_port.CubePadPort(info["pad"])(x)[:, 0].numpy().astype(np.int32)
+        assert sha(y) == info["sha256"], key
+    for kat in golden_meta["cubepad_kat"]:
+        x = torch.arange(int(np.prod(kat["shape"])), dtype=torch.float32).reshape(kat["shape"])
+        assert sha(ref_port.CubePadPort(kat["pad"])(x).numpy()) == kat["sha256"]
+    with pytest.raises(ValueError):
+        ref_port.CubePadPort(1)(torch.zeros(5, 1, 4, 4))
+
+
+def test_ref_port_e2c_c2e(golden_meta, golden_small):
+    import torch
+    from oracle import ref_port
+    cv2 = pytest.importorskip("cv2")
+    for key, info in golden_meta["e2c"].items():
+        if info["w"] > 64:
+            continue
+        img = np.random.default_rng(info["seed"]).random((info["H"], info["W"], 3), dtype=np.float32)
+        faces = ref_port.Equi2CubePort(info["w"], info["H"], info["W"], info["vfov"]).to_cube(img)
+        assert sha(np.stack([faces[i] for i in range(6)])) == info["faces_sha256"], key
+    for key, info in golden_meta["c2e"].items():
+        if key + "_out" not in golden_small.files:
+            continue
+        cube = np.random.default_rng(info["seed"]).standard_normal((6, info["C"], info["w"], info["w"])).astype(np.float32)
+        port = ref_port.Cube2EquiPort(info["w"])
+        out = port.to_equi_nn(torch.from_numpy(cube)).numpy()
+        assert np.abs(out - golden_small[key + "_out"]).max() <= 4e-6, key
+        np.testing.assert_array_equal(port.to_equi_max(torch.from_numpy(cube)).numpy(), out[0].max(axis=0))
