@@ -22,7 +22,7 @@ SIGNATURES = {
     "cp360_cubepad_build_map": (c_i32, [c_i32] * 6 + [c_vp]),
     "cp360_cubepad_fwd": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 7 + [c_vp]),
     "cp360_cubepad_fwd_algo": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 8 + [c_vp]),
-    "cp360_cubepad_pick_algo": (c_i32, [c_i64] + [c_i32] * 8),
+    "cp360_cubepad_pick_algo": (c_i32, [c_i64, c_i64] + [c_i32] * 8),
     "cp360_cubepad_bwd_f32": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 6 + [c_vp]),
     "cp360_e2c_build_map": (c_i32, [c_i32, c_i32, c_i32, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cp360_e2c_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
@@ -36,7 +36,7 @@ SIGNATURES = {
 CP360_OK = 0
 CP360_ERR_GROUP = 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-ALGO_AUTO, ALGO_GENERIC, ALGO_BAND_STG, ALGO_BAND_BULK, ALGO_CUBE = range(5)
+ALGO_AUTO, ALGO_GENERIC, ALGO_BAND_STG, ALGO_BAND_BULK, ALGO_CUBE, ALGO_ROW = range(6)
 
 _lock = threading.Lock()
 _lib = None

@@ -19,14 +19,17 @@
 // The geometry is the 4x6 affine plate table of cubepad_geom.h, identical for all kernels and
 // for the host-side index map exported to the parity tests.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "cubepad_geom.h"
 #include "tma.cuh"
+#include "cubepad_row.cuh"
 
 namespace cp360 {
 
-enum CubePadAlgo { ALGO_AUTO = 0, ALGO_GENERIC = 1, ALGO_BAND_STG = 2, ALGO_BAND_BULK = 3, ALGO_CUBE = 4 };
+enum CubePadAlgo { ALGO_AUTO = 0, ALGO_GENERIC = 1, ALGO_BAND_STG = 2, ALGO_BAND_BULK = 3, ALGO_CUBE = 4,
+                   ALGO_ROW = 5 };
 
 // ------------------------------------------------------------------------------------------
 // generic: any element type
@@ -427,6 +430,61 @@ static int launch_band(const void* x, void* y, int64_t n_planes, int C, const Cu
   return CP360_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// Tiling of the row kernel. Returns false if it does not apply.
+static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) {
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  if (n_planes <= 0 || n_planes > 0x3fffffff) return false;
+  if ((n_planes * HW) % 4) return false;                       // input ends on a 16 B boundary
+  const int target_words = std::max(1, env_int("CP360_ROW_TILE_KB", 4)) * 256;
+  a->C = C;
+  a->n_planes = (int32_t)n_planes;
+  a->total_in_words = n_planes * HW;
+  if (HW > target_words + target_words / 2) {                  // bands of rows inside one plane
+    const int rb0 = std::max(1, target_words / g.W);
+    a->nb = (g.Ho + rb0 - 1) / rb0;
+    a->Rb = (g.Ho + a->nb - 1) / a->nb;
+    a->nb = (g.Ho + a->Rb - 1) / a->Rb;
+    a->k = 1;
+    a->slot_words = ((a->Rb * g.W + 8) + 31) & ~31;
+    if (n_planes * a->nb > 0x7fffffff) return false;
+    a->n_tiles = (int32_t)(n_planes * a->nb);
+  } else {                                                     // k whole planes per tile
+    a->nb = 1;
+    a->Rb = g.Ho;
+    a->k = std::max(1, target_words / HW);
+    a->slot_words = ((a->k * HW + 8) + 31) & ~31;
+    a->n_tiles = (int32_t)((n_planes + a->k - 1) / a->k);
+  }
+  a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 2)));
+  a->any_corner_lr = g.corner_uses_lr[0] | g.corner_uses_lr[1] | g.corner_uses_lr[2] | g.corner_uses_lr[3];
+  (void)HoWo;
+  return true;
+}
+
+static int launch_row(const void* x, void* y, int64_t n_planes, int C, const CubePadGeom& g,
+                      cudaStream_t st) {
+  RowArgs a;
+  CP360_CHECK_ARG(row_plan(g, n_planes, C, &a), CP360_ERR_SHAPE,
+                  "row kernel does not apply (H=%d, planes=%lld)", g.H, (long long)n_planes);
+  a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
+  const size_t smem = kRowBarBytes + (size_t)kRowWarps * a.slots * a.slot_words * 4;
+  CP360_CHECK_ARG(smem <= 220 * 1024, CP360_ERR_SHAPE, "row kernel tile too large");
+  CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  int per_sm = std::max(1, std::min(2048 / kRowThreads, (int)((224 * 1024) / (smem + 1024))));
+  per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 8)));
+  const int64_t ctas_needed = ((int64_t)a.n_tiles + kRowWarps - 1) / kRowWarps;
+  const int64_t grid = std::min<int64_t>(ctas_needed, (int64_t)sm_count() * per_sm);
+  cubepad_row_kernel<<<(unsigned)grid, kRowThreads, smem, st>>>(a, g);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
 static int validate(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
                     int pr, int pt, int pd, CubePadGeom* g) {
   CP360_CHECK_ARG(n_faces >= 0 && C >= 0, CP360_ERR_BAD_ARG, "negative size");
@@ -442,10 +500,11 @@ static int validate(const void* x, void* y, int64_t n_faces, int64_t C, int H, i
   return CP360_OK;
 }
 
-static int pick_algo(const CubePadGeom& g, int C, bool fast_ok) {
-  int k; size_t smem;
+static int pick_algo(const CubePadGeom& g, int64_t n_faces, int C, bool fast_ok) {
+  int k; size_t smem; RowArgs ra;
+  if (fast_ok && g.H >= 24 && row_plan(g, n_faces * C, C, &ra)) return ALGO_ROW;
   if (fast_ok && g.H <= 32 && cube_plan(g, C, &k, &smem)) return ALGO_CUBE;
-  if (fast_ok && band_ok(g) && g.H >= 24) return ALGO_BAND_BULK;
+  if (fast_ok && g.H >= 24 && band_ok(g)) return ALGO_BAND_BULK;
   return ALGO_GENERIC;
 }
 
@@ -479,14 +538,14 @@ int cp360_cubepad_build_map(int H, int W, int pl, int pr, int pt, int pd, int32_
   return CP360_OK;
 }
 
-int cp360_cubepad_pick_algo(int64_t C, int H, int W, int pl, int pr, int pt, int pd, int elem_bytes,
-                            int aligned16) {
+int cp360_cubepad_pick_algo(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,
+                            int elem_bytes, int aligned16) {
   CubePadGeom g;
   if (!make_geom(H, W, pl, pr, pt, pd, &g) || C < 0 || C > 0x7fffffff) {
     set_error("CubePad needs square faces and 0 <= pad <= H");
     return -CP360_ERR_SHAPE;
   }
-  return pick_algo(g, (int)C, elem_bytes == 4 && aligned16 != 0);
+  return pick_algo(g, n_faces, (int)C, elem_bytes == 4 && aligned16 != 0);
 }
 
 int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
@@ -506,7 +565,7 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
   const int64_t n_planes = n_faces * C;
   const bool fast_ok = elem_bytes == 4 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
 
-  if (algo == ALGO_AUTO) algo = pick_algo(g, (int)C, fast_ok);
+  if (algo == ALGO_AUTO) algo = pick_algo(g, n_faces, (int)C, fast_ok);
   switch (algo) {
     case ALGO_CUBE:
       CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "cube-tile kernel needs 4-byte elements, 16 B aligned");
@@ -515,6 +574,9 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
     case ALGO_BAND_BULK:
       CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "band kernel needs 4-byte elements, 16 B aligned");
       return launch_band(x, y, n_planes, (int)C, g, algo == ALGO_BAND_BULK, st);
+    case ALGO_ROW:
+      CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "row kernel needs 4-byte elements, 16 B aligned");
+      return launch_row(x, y, n_planes, (int)C, g, st);
     case ALGO_GENERIC:
       switch (elem_bytes) {
         case 1: return launch_generic<uint8_t>(x, y, n_planes, (int)C, g, st);

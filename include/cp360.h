@@ -83,14 +83,14 @@ CP360_API int cp360_cubepad_fwd(const void* x_dev, void* y_dev, int64_t n_faces,
 
 /* Same, with the kernel forced (tests / benchmarks): 0 auto, 1 generic gather, 2 band kernel with
  * streaming stores, 3 band kernel with TMA bulk stores, 4 cube-tile kernel (all six faces of a
- * channel group staged in shared memory). Non-applicable choices return CP360_ERR_SHAPE/ALIGN. */
+ * channel group staged in shared memory), 5 row kernel (TMA bulk loads, warp-specialised). Non-applicable choices return CP360_ERR_SHAPE/ALIGN. */
 CP360_API int cp360_cubepad_fwd_algo(const void* x_dev, void* y_dev, int64_t n_faces, int64_t C, int H, int W,
                            int pl, int pr, int pt, int pd, int elem_bytes, int algo, void* stream);
 
 /* Host: the kernel cp360_cubepad_fwd (algo 0) runs for this problem: 1 generic, 3 band, 4
- * cube-tile; aligned16 = both tensor pointers are 16 B aligned. Negative: -status. */
-CP360_API int cp360_cubepad_pick_algo(int64_t C, int H, int W, int pl, int pr, int pt, int pd,
-                            int elem_bytes, int aligned16);
+ * cube-tile, 5 row; aligned16 = both tensor pointers are 16 B aligned. Negative: -status. */
+CP360_API int cp360_cubepad_pick_algo(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt,
+                            int pd, int elem_bytes, int aligned16);
 
 /* Device, fp32: gx[6N,C,H,W] = dCubePad^T(gy[6N,C,Ho,Wo]) — every input pixel receives the sum
  * of the gradients of all output pixels that copied it (what autograd derives from the

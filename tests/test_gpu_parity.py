@@ -45,7 +45,8 @@ def gather_reference(x, imap):
     return out.reshape(n6, C, Ho, Wo).contiguous()
 
 
-ALGOS = [_lib.ALGO_AUTO, _lib.ALGO_GENERIC, _lib.ALGO_BAND_STG, _lib.ALGO_BAND_BULK, _lib.ALGO_CUBE]
+ALGOS = [_lib.ALGO_AUTO, _lib.ALGO_GENERIC, _lib.ALGO_BAND_STG, _lib.ALGO_BAND_BULK, _lib.ALGO_CUBE,
+         _lib.ALGO_ROW]
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmark (GPU box): GB/s of every kernel variant at the BASELINE shapes,
+beside a plain device copy of comparable size. Development tool; bench.py is the contract.
+
+    python tools/kbench.py [--batch 16] [--iters 20] [--only cubepad|e2c|c2e]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import cp360_b200  # noqa: E402
+from cp360_b200 import _lib  # noqa: E402
+
+
+def timeit(fn, iters, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    B = args.batch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
+    rows = []
+
+    def report(name, nbytes, ms):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows.append({"name": name, "MB": round(nbytes / 1e6, 2), "us": round(ms * 1e3, 1), "GB/s": round(gbs, 1)})
+        print("%-58s %9.2f MB %9.1f us %8.1f GB/s" % (name, nbytes / 1e6, ms * 1e3, gbs), flush=True)
+
+    # plain copies for scale
+    for mb in (8, 64, 512):
+        a = torch.empty(mb << 18, dtype=torch.float32, device=dev)
+        b = torch.empty_like(a)
+        report("torch copy %d MB" % mb, 2 * a.numel() * 4, timeit(lambda: b.copy_(a), args.iters, flush))
+
+    if args.only in ("", "cubepad"):
+        sites = []
+        for s in cp360_b200.resnet50_cubepad_sites(256) + [(2048, 8, 1), (64, 256, 2)] + \
+                cp360_b200.resnet50_cubepad_sites(224) + [(2000, 7, 1), (4000, 7, 1)]:
+            if s not in sites:
+                sites.append(s)
+        for C, H, p in sites:
+            n = 6 * B if (C, H) != (64, 256) else 12
+            x = torch.randn(n, C, H, H, device=dev)
+            nbytes = n * C * (H * H + (H + 2 * p) ** 2) * 4
+            for algo, an in ((1, "generic"), (3, "band_bulk"), (4, "cube"), (5, "row")):
+                try:
+                    cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
+                except _lib.CP360Error:
+                    continue
+                auto = _lib.lib().cp360_cubepad_pick_algo(n, C, H, H, p, p, p, p, 4, 1) == algo
+                y = torch.empty(n, C, H + 2 * p, H + 2 * p, device=dev)
+                st = torch.cuda.current_stream().cuda_stream
+
+                def fn():
+                    _lib.lib().cp360_cubepad_fwd_algo(x.data_ptr(), y.data_ptr(), n, C, H, H, p, p, p, p, 4, algo, st)
+                report("cubepad [%d,%d,%d,%d] p%d %s%s" % (n, C, H, H, p, an, " *" if auto else ""), nbytes,
+                       timeit(fn, args.iters, flush))
+            del x
+
+    if args.only in ("", "e2c"):
+        pipe = cp360_b200.SphericalPipeline(device=dev)
+        for w in (256, 224):
+            import numpy as np
+            e2c = cp360_b200.Equi2Cube(w, np.empty((960, 1920, 3), np.float32))
+            frames = torch.rand(B, 960, 1920, 3, device=dev)
+            out = torch.empty(6 * B, 3, w, w, device=dev)
+            pipe.e2c, pipe.cube = e2c, w
+            nb = pipe.e2c_bytes_per_frame() * B
+            report("e2c 1920x960 -> %d NCHW B=%d" % (w, B), nb,
+                   timeit(lambda: e2c.to_cube_tensor(frames, out=out), args.iters, flush))
+            report("e2c 1920x960 -> %d NCHW+norm B=%d" % (w, B), nb,
+                   timeit(lambda: e2c.to_cube_tensor(frames, out=out, mean=[.485, .456, .406], std=[.229, .224, .225]),
+                          args.iters, flush))
+
+    if args.only in ("", "c2e"):
+        for w, C in ((8, 1000), (8, 2048), (7, 1000), (16, 256), (64, 64), (256, 8)):
+            bb = B if w <= 16 else 2
+            c2e = cp360_b200.Cube2Equi(w)
+            x = torch.randn(6 * bb, C, w, w, device=dev)
+            report("c2e      [%d,%d,%d,%d]" % (6 * bb, C, w, w), bb * C * 14 * w * w * 4,
+                   timeit(lambda: c2e.to_equi_nn(x), args.iters, flush))
+            report("c2e+max  [%d,%d,%d,%d]" % (6 * bb, C, w, w), bb * (C * 6 * w * w * 4 + 8 * w * w * 4),
+                   timeit(lambda: c2e.to_equi_max(x), args.iters, flush))
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Run one kernel a few times (for ncu): python tools/prof_one.py cubepad C H p [algo] [B]
+                                          python tools/prof_one.py e2c w [B] | c2e w C [B] | c2emax w C [B]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import cp360_b200
+
+kind = sys.argv[1]
+dev = torch.device("cuda", 0)
+if kind == "cubepad":
+    C, H, p = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    algo = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    B = int(sys.argv[6]) if len(sys.argv) > 6 else 16
+    x = torch.randn(6 * B, C, H, H, device=dev)
+    for _ in range(3):
+        y = cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
+elif kind == "e2c":
+    w = int(sys.argv[2]); B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    e2c = cp360_b200.Equi2Cube(w, np.empty((960, 1920, 3), np.float32))
+    fr = torch.rand(B, 960, 1920, 3, device=dev)
+    for _ in range(3):
+        e2c.to_cube_tensor(fr)
+else:
+    w, C = int(sys.argv[2]), int(sys.argv[3]); B = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+    c2e = cp360_b200.Cube2Equi(w)
+    x = torch.randn(6 * B, C, w, w, device=dev)
+    for _ in range(3):
+        (c2e.to_equi_max if kind == "c2emax" else c2e.to_equi_nn)(x)
+torch.cuda.synchronize()
