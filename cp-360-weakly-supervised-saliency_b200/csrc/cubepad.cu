@@ -460,8 +460,12 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
     a->slot_words = ((a->k * HW + 8) + 31) & ~31;
     a->n_tiles = (int32_t)((n_planes + a->k - 1) / a->k);
   }
-  a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 2)));
+  a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 3)));
   a->any_corner_lr = g.corner_uses_lr[0] | g.corner_uses_lr[1] | g.corner_uses_lr[2] | g.corner_uses_lr[3];
+  a->d_nb = make_fastdiv((uint32_t)a->nb);
+  a->d_C = make_fastdiv((uint32_t)C);
+  a->d_nside = make_fastdiv((uint32_t)std::max(1, g.pl + g.pr));
+  a->d_Wo = make_fastdiv((uint32_t)g.Wo);
   (void)HoWo;
   return true;
 }
@@ -474,13 +478,23 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
   const size_t smem = kRowBarBytes + (size_t)kRowWarps * a.slots * a.slot_words * 4;
   CP360_CHECK_ARG(smem <= 220 * 1024, CP360_ERR_SHAPE, "row kernel tile too large");
-  CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+  void (*kern)(const RowArgs, const CubePadGeom) = cubepad_row_kernel<0, false>;
+  const int nj = (g.W + 31) / 32;
+  const bool full = g.W % 32 == 0;
+  switch (nj) {
+    case 1: kern = full ? cubepad_row_kernel<1, true> : cubepad_row_kernel<1, false>; break;
+    case 2: kern = full ? cubepad_row_kernel<2, true> : cubepad_row_kernel<2, false>; break;
+    case 4: kern = full ? cubepad_row_kernel<4, true> : cubepad_row_kernel<4, false>; break;
+    case 7: if (!full) kern = cubepad_row_kernel<7, false>; break;
+    case 8: if (full) kern = cubepad_row_kernel<8, true>; break;
+    default: break;
+  }
+  CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = std::max(1, std::min(2048 / kRowThreads, (int)((224 * 1024) / (smem + 1024))));
   per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 8)));
   const int64_t ctas_needed = ((int64_t)a.n_tiles + kRowWarps - 1) / kRowWarps;
   const int64_t grid = std::min<int64_t>(ctas_needed, (int64_t)sm_count() * per_sm);
-  cubepad_row_kernel<<<(unsigned)grid, kRowThreads, smem, st>>>(a, g);
+  kern<<<(unsigned)grid, kRowThreads, smem, st>>>(a, g);
   CP360_LAUNCHED();
   return CP360_OK;
 }

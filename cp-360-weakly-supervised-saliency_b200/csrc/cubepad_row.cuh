@@ -15,6 +15,7 @@
 // The few elements that are not a straight copy (side columns, top/bottom pad rows, corners) are
 // gathered from L2 through the affine plate table; their loads are issued BEFORE the warp waits
 // for its tile and consumed after the rows are copied, so their latency hides behind the copy.
+// Integer divisions by run-time constants use host-computed multiply-shift pairs.
 #pragma once
 #include "common.cuh"
 #include "cubepad_geom.h"
@@ -26,6 +27,23 @@ constexpr int kRowWarps = 8;
 constexpr int kRowThreads = kRowWarps * 32;
 constexpr int kRowMaxSlots = 8;
 constexpr int kRowBarBytes = kRowWarps * kRowMaxSlots * 8;
+
+// n / d for 0 <= n < 2^31 as umulhi(n, m) >> s  (m == 0: d == 1)
+struct FastDiv { uint32_t m, s; };
+
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f = {0u, 0u};
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                       // smallest l with 2^l >= d
+  f.m = (uint32_t)(((1ull << (31 + l)) / d) + 1);    // < 2^32 because d > 2^(l-1)
+  f.s = l - 1;
+  return f;
+}
+
+__device__ __forceinline__ int fdiv(int n, const FastDiv& d) {
+  return d.m ? (int)(__umulhi((uint32_t)n, d.m) >> d.s) : n;
+}
 
 struct RowArgs {
   const uint32_t* x;
@@ -40,6 +58,7 @@ struct RowArgs {
   int32_t slot_words;       // capacity of one ring slot
   int32_t slots;
   int32_t any_corner_lr;    // some corner repeats the l/r plate (asymmetric pads only)
+  FastDiv d_nb, d_C, d_nside, d_Wo;
 };
 
 struct RowTile {
@@ -54,7 +73,7 @@ struct RowTile {
 __device__ __forceinline__ RowTile row_tile(const RowArgs& a, const CubePadGeom& g, int t) {
   RowTile d;
   if (a.nb > 1) {
-    d.p0 = t / a.nb;
+    d.p0 = fdiv(t, a.d_nb);
     const int b = t - d.p0 * a.nb;
     d.np = 1;
     d.oyA = b * a.Rb;
@@ -89,6 +108,57 @@ __device__ __forceinline__ int row_pad_src(const RowArgs& a, const CubePadGeom& 
   return m.base + m.sr * r + m.sc * cc;
 }
 
+// nr rows of W words: sp (shared, row pitch W) -> dp (global, row pitch Wo); both already
+// offset by the lane. NJ = ceil(W / 32) at compile time (0: run-time loop); FULL: W % 32 == 0.
+template <int NJ, bool FULL>
+__device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32_t* __restrict__ dp,
+                                         int nr, int W, int Wo, int lane) {
+  if (NJ == 0) {
+    for (int r = 0; r < nr; ++r, sp += W, dp += Wo)
+      for (int jj = 0; jj + lane < W; jj += 32) __stcs(dp + jj, sp[jj]);
+    return;
+  }
+  constexpr int NJc = NJ > 0 ? NJ : 1;
+  const bool tail_ok = FULL || (NJc - 1) * 32 + lane < W;
+  if (NJc >= 4) {
+    // wide rows: one row per step, NJ loads in flight
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r, sp += W, dp += Wo) {
+      uint32_t v[NJc];
+#pragma unroll
+      for (int j = 0; j < NJc; ++j)
+        if (j < NJc - 1 || tail_ok) v[j] = sp[j * 32];
+#pragma unroll
+      for (int j = 0; j < NJc; ++j)
+        if (j < NJc - 1 || tail_ok) __stcs(dp + j * 32, v[j]);
+    }
+  } else {
+    // narrow rows: four rows per step
+    int r = 0;
+#pragma unroll 1
+    for (; r + 4 <= nr; r += 4, sp += 4 * W, dp += 4 * Wo) {
+      uint32_t v[4][NJc];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NJc; ++j)
+          if (j < NJc - 1 || tail_ok) v[k][j] = sp[k * W + j * 32];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NJc; ++j)
+          if (j < NJc - 1 || tail_ok) __stcs(dp + k * Wo + j * 32, v[k][j]);
+    }
+#pragma unroll 1
+    for (; r < nr; ++r, sp += W, dp += Wo) {
+#pragma unroll
+      for (int j = 0; j < NJc; ++j)
+        if (j < NJc - 1 || tail_ok) __stcs(dp + j * 32, sp[j * 32]);
+    }
+  }
+}
+
+template <int NJ, bool FULL>
 __global__ void __launch_bounds__(kRowThreads)
 cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -105,7 +175,7 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   auto issue = [&](int t, int s) {
     const RowTile d = row_tile(a, g, t);
     tma::mbar_expect_tx(&bar[s], (uint32_t)d.words * 4u);
-    if (d.words) tma::bulk_load(ring + (size_t)s * a.slot_words, a.x + d.w0, (uint32_t)d.words * 4u, &bar[s]);
+    if (d.words) tma::bulk_load(ring + s * a.slot_words, a.x + d.w0, (uint32_t)d.words * 4u, &bar[s]);
   };
 
   if (lane == 0) {
@@ -116,84 +186,76 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   }
   __syncwarp();
 
-  int it = 0;
-  for (int t = gw; t < a.n_tiles; t += GW, ++it) {
-    const int s = it % slots;
+  int s = 0;
+  uint32_t phase = 0;
+#pragma unroll 1
+  for (int t = gw; t < a.n_tiles; t += GW) {
     const RowTile d = row_tile(a, g, t);
-    const uint32_t* in_s = ring + (size_t)s * a.slot_words + d.shift;
-    int nf = d.p0 / a.C, c = d.p0 - nf * a.C, f = nf % 6;
+    const uint32_t* in_s = ring + s * a.slot_words + d.shift;
+    int nf = fdiv(d.p0, a.d_C), c = d.p0 - nf * a.C, f = nf % 6;
     const int ntop = max(min(d.oyB, g.pt) - d.oyA, 0);
     const int bot0 = max(d.oyA, g.pt + H), nbot = max(d.oyB - bot0, 0);
     const int n_side = (d.yb - d.ya) * nside, n_pad = (ntop + nbot) * Wo;
 
-    uint32_t hv0 = 0, hv1 = 0;                 // gathered values in flight
-    uint32_t *hp0 = nullptr, *hp1 = nullptr;   // where they go
+    const int n_halo = n_side + n_pad;
     bool landed = false;
+#pragma unroll 1
     for (int j = 0; j < d.np; ++j) {
       const uint32_t* __restrict__ cube = a.x + ((int64_t)(nf - f) * a.C + c) * HW;
       uint32_t* __restrict__ outp = a.y + (int64_t)(d.p0 + j) * HoWo;
 
-      // ---- A. side columns of the interior rows: lanes = (row, side column)
-      for (int q0 = 0; q0 < n_side; q0 += 32) {
-        if (hp0) { __stcs(hp0, hv0); hp0 = nullptr; }
-        const int q = q0 + lane;
-        if (q < n_side) {
-          const int i = q / nside, sc = q - i * nside, y = d.ya + i;
-          const bool left = sc < g.pl;
-          const PlateMap& m = g.plate[left ? P_LEFT : P_RIGHT][f];
-          const int pix = m.base + m.sr * y + m.sc * (left ? sc : sc - g.pl);
-          hv0 = __ldg(cube + m.face * face_stride + pix);
-          hp0 = outp + (y + g.pt) * Wo + (left ? sc : W + sc);
-        }
-      }
-      // ---- B. top / bottom pad rows (incl. corners) of this band
-      for (int q0 = 0; q0 < n_pad; q0 += 32) {
-        if (hp1) { __stcs(hp1, hv1); hp1 = nullptr; }
-        const int q = q0 + lane;
-        if (q < n_pad) {
-          const int rr = q / Wo, ox = q - rr * Wo;
-          const int oy = rr < ntop ? d.oyA + rr : bot0 + (rr - ntop);
-          int sf;
-          const int pix = row_pad_src(a, g, f, oy, ox, &sf);
-          hv1 = __ldg(cube + sf * face_stride + pix);
-          hp1 = outp + oy * Wo + ox;
-        }
-      }
-      // ---- C. interior rows: shifted copy shared -> global
-      if (!landed) { tma::mbar_wait(&bar[s], (uint32_t)((it / slots) & 1)); landed = true; }
-      const uint32_t* __restrict__ sp = in_s + j * HW + lane;
-      uint32_t* __restrict__ dp = outp + (d.ya + g.pt) * Wo + g.pl + lane;
-      const int nr = d.yb - d.ya;
-      int r = 0;
-      if (W >= 128) {
-        for (; r < nr; ++r, sp += W, dp += Wo) {
-          int jj = 0;
-          for (; jj + 96 + lane < W; jj += 128) {
-            const uint32_t v0 = sp[jj], v1 = sp[jj + 32], v2 = sp[jj + 64], v3 = sp[jj + 96];
-            __stcs(dp + jj, v0); __stcs(dp + jj + 32, v1); __stcs(dp + jj + 64, v2); __stcs(dp + jj + 96, v3);
-          }
-          for (; jj + lane < W; jj += 32) __stcs(dp + jj, sp[jj]);
-        }
-      } else {
-        for (; r + 4 <= nr; r += 4, sp += 4 * W, dp += 4 * Wo) {
-          for (int jj = 0; jj + lane < W; jj += 32) {
-            const uint32_t v0 = sp[jj], v1 = sp[jj + W], v2 = sp[jj + 2 * W], v3 = sp[jj + 3 * W];
-            __stcs(dp + jj, v0); __stcs(dp + jj + Wo, v1); __stcs(dp + jj + 2 * Wo, v2); __stcs(dp + jj + 3 * Wo, v3);
+      // ---- A. everything that is not a straight row copy — side columns of the interior rows,
+      //         then the top / bottom pad rows incl. corners — as one list, four gathers per lane
+      //         in flight. The first batch is issued before the tile is awaited and stored after
+      //         its rows are copied.
+      uint32_t hv[4];
+      int ho[4];
+      auto gather = [&](int q0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * 32 + lane;
+          ho[u] = -1;
+          if (q < n_side) {
+            const int i = fdiv(q, a.d_nside), sc = q - i * nside, y = d.ya + i;
+            const bool left = sc < g.pl;
+            const PlateMap& m = g.plate[left ? P_LEFT : P_RIGHT][f];
+            const int pix = m.base + m.sr * y + m.sc * (left ? sc : sc - g.pl);
+            hv[u] = __ldg(cube + m.face * face_stride + pix);
+            ho[u] = (y + g.pt) * Wo + (left ? sc : W + sc);
+          } else if (q < n_halo) {
+            const int qp = q - n_side;
+            const int rr = fdiv(qp, a.d_Wo), ox = qp - rr * Wo;
+            const int oy = rr < ntop ? d.oyA + rr : bot0 + (rr - ntop);
+            int sf;
+            const int pix = row_pad_src(a, g, f, oy, ox, &sf);
+            hv[u] = __ldg(cube + sf * face_stride + pix);
+            ho[u] = oy * Wo + ox;
           }
         }
-        for (; r < nr; ++r, sp += W, dp += Wo)
-          for (int jj = 0; jj + lane < W; jj += 32) __stcs(dp + jj, sp[jj]);
+      };
+      auto flush = [&]() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ho[u] >= 0) __stcs(outp + ho[u], hv[u]);
+      };
+      gather(0);
+      // ---- B. interior rows: shifted copy shared -> global
+      if (!landed) { tma::mbar_wait(&bar[s], phase); landed = true; }
+      row_copy<NJ, FULL>(in_s + j * HW + lane, outp + (d.ya + g.pt) * Wo + g.pl + lane, d.yb - d.ya, W, Wo,
+                         lane);
+      if (j == d.np - 1) {
+        __syncwarp();                              // every lane is done reading slot s:
+        if (lane == 0) {                           // re-arm it with the tile `slots` steps ahead
+          const int tn = t + slots * GW;
+          if (tn < a.n_tiles) issue(tn, s);
+        }
       }
+      flush();
+#pragma unroll 1
+      for (int q0 = 128; q0 < n_halo; q0 += 128) { gather(q0); flush(); }
       if (++c == a.C) { c = 0; ++nf; if (++f == 6) f = 0; }
     }
-    if (!landed) tma::mbar_wait(&bar[s], (uint32_t)((it / slots) & 1));   // keep the phases in step
-    __syncwarp();                                  // every lane is done reading slot s
-    if (lane == 0) {
-      const int tn = t + slots * GW;
-      if (tn < a.n_tiles) issue(tn, s);
-    }
-    if (hp0) __stcs(hp0, hv0);
-    if (hp1) __stcs(hp1, hv1);
+    if (++s == slots) { s = 0; phase ^= 1u; }
   }
 }
 
