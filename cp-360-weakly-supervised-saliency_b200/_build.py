@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libcp360.so")
+LIB_PATH = os.environ.get("CP360_LIB") or os.path.join(LIB_DIR, "libcp360.so")   # CP360_LIB: dev override
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 CU_SOURCES = ["common.cu", "cubepad.cu", "e2c.cu", "c2e.cu"]
@@ -59,7 +59,7 @@ def build_library(force=False, verbose=False):
     jobs = []
     for src in CU_SOURCES:
         obj = os.path.join(OBJ_DIR, src + ".o")
-        jobs.append(([nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], obj))
+        jobs.append(([nvcc] + NVCC_FLAGS + os.environ.get("CP360_NVCC_EXTRA", "").split() + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], obj))
     for src in CPP_SOURCES:
         obj = os.path.join(OBJ_DIR, src + ".o")
         jobs.append((["g++"] + CXX_FLAGS + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], obj))

@@ -437,36 +437,42 @@ static int env_int(const char* name, int dflt) {
 
 // Tiling of the row kernel. Returns false if it does not apply.
 static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) {
-  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  const int HW = g.H * g.W;
   if (n_planes <= 0 || n_planes > 0x3fffffff) return false;
   if ((n_planes * HW) % 4) return false;                       // input ends on a 16 B boundary
   const int target_words = std::max(1, env_int("CP360_ROW_TILE_KB", 4)) * 256;
   a->C = C;
   a->n_planes = (int32_t)n_planes;
   a->total_in_words = n_planes * HW;
-  if (HW > target_words + target_words / 2) {                  // bands of rows inside one plane
-    const int rb0 = std::max(1, target_words / g.W);
-    a->nb = (g.Ho + rb0 - 1) / rb0;
-    a->Rb = (g.Ho + a->nb - 1) / a->nb;
-    a->nb = (g.Ho + a->Rb - 1) / a->Rb;
+  const int rb_env = env_int("CP360_ROW_RB", 0);
+  if ((rb_env > 0 && rb_env < g.H) || (rb_env == 0 && HW > target_words + target_words / 2)) {   // bands of rows inside one plane
+    // ~4.5 KB tiles (5 KB for narrow rows) measured best on B200; see profiles/README.md
+    int rb = std::max(1, (target_words + target_words / 8) / g.W);
+    if (g.W < 128) rb = std::max(4, (target_words + target_words / 4) / g.W / 4 * 4);   // narrow rows: copied four at a time
+    if (rb_env > 0) rb = rb_env;
+    a->Rb = rb;
+    while ((g.H + rb - 1) / rb > 256) ++rb;                    // push-range table: 6 * nb * 16 B of shared memory
+    a->nb = (g.H + rb - 1) / rb;
     a->k = 1;
-    a->slot_words = ((a->Rb * g.W + 8) + 31) & ~31;
-    if (n_planes * a->nb > 0x7fffffff) return false;
-    a->n_tiles = (int32_t)(n_planes * a->nb);
+    // a warp walks `ub` consecutive bands; keep >= ~16 units per warp for load balance
+    const int64_t warps = (int64_t)sm_count() * kRowWarps;
+    int ub = std::max(1, env_int("CP360_ROW_UNIT_BANDS", 1));
+    while (ub > 1 && n_planes * ((a->nb + ub - 1) / ub) < 16 * warps) ub >>= 1;
+    a->ub = std::min(ub, a->nb);
+    a->upp = (a->nb + a->ub - 1) / a->ub;
+    a->slot_words = ((rb * g.W + 8) + 31) & ~31;
+    if (n_planes * a->upp > 0x7fffffff) return false;
+    a->n_units = (int32_t)(n_planes * a->upp);
   } else {                                                     // k whole planes per tile
-    a->nb = 1;
-    a->Rb = g.Ho;
+    a->nb = 1; a->ub = 1; a->upp = 1;
+    a->Rb = g.H;
     a->k = std::max(1, target_words / HW);
     a->slot_words = ((a->k * HW + 8) + 31) & ~31;
-    a->n_tiles = (int32_t)((n_planes + a->k - 1) / a->k);
+    a->n_units = (int32_t)((n_planes + a->k - 1) / a->k);
   }
   a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 3)));
-  a->any_corner_lr = g.corner_uses_lr[0] | g.corner_uses_lr[1] | g.corner_uses_lr[2] | g.corner_uses_lr[3];
-  a->d_nb = make_fastdiv((uint32_t)a->nb);
+  a->d_upp = make_fastdiv((uint32_t)a->upp);
   a->d_C = make_fastdiv((uint32_t)C);
-  a->d_nside = make_fastdiv((uint32_t)std::max(1, g.pl + g.pr));
-  a->d_Wo = make_fastdiv((uint32_t)g.Wo);
-  (void)HoWo;
   return true;
 }
 
@@ -476,7 +482,11 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   CP360_CHECK_ARG(row_plan(g, n_planes, C, &a), CP360_ERR_SHAPE,
                   "row kernel does not apply (H=%d, planes=%lld)", g.H, (long long)n_planes);
   a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
-  const size_t smem = kRowBarBytes + (size_t)kRowWarps * a.slots * a.slot_words * 4;
+  const int align = std::max(16, env_int("CP360_ROW_SMEM_ALIGN", 128));
+  a.ring_off = (int)((kRowBarBytes + 6 * a.nb * 16 + align - 1) / align * align) + env_int("CP360_ROW_SMEM_PAD", 0);
+  const int slot_align = std::max(32, env_int("CP360_ROW_SLOT_ALIGN_WORDS", 32));
+  a.slot_words = (a.slot_words + slot_align - 1) / slot_align * slot_align;
+  const size_t smem = (size_t)a.ring_off + (size_t)kRowWarps * a.slots * a.slot_words * 4;
   CP360_CHECK_ARG(smem <= 220 * 1024, CP360_ERR_SHAPE, "row kernel tile too large");
   void (*kern)(const RowArgs, const CubePadGeom) = cubepad_row_kernel<0, false>;
   const int nj = (g.W + 31) / 32;
@@ -491,8 +501,8 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   }
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = std::max(1, std::min(2048 / kRowThreads, (int)((224 * 1024) / (smem + 1024))));
-  per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 8)));
-  const int64_t ctas_needed = ((int64_t)a.n_tiles + kRowWarps - 1) / kRowWarps;
+  per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 1)));
+  const int64_t ctas_needed = ((int64_t)a.n_units + kRowWarps - 1) / kRowWarps;
   const int64_t grid = std::min<int64_t>(ctas_needed, (int64_t)sm_count() * per_sm);
   kern<<<(unsigned)grid, kRowThreads, smem, st>>>(a, g);
   CP360_LAUNCHED();

@@ -28,10 +28,28 @@ struct PlateMap {      // source = (face, pix) with pix = base + sr*r + sc*c  (p
   int32_t sc;          // yc*W + xc
 };
 
+// The same geometry seen from the SOURCE side ("push" form, used by the row kernel): face f is the
+// source of exactly four plates of other faces. Entry k of face f describes one of them as a
+// rectangle of destination elements (u, v) in [0,U) x [0,V) at (oy0 + u, ox0 + v) of face `dface`
+// — the plate plus the corner elements that replicate its edge — and the affine map from plate
+// coordinates to the source pixel:
+//     cmode 0 (top/down plates):   r = u,                        c = clamp(v + off, 0, W-1)
+//     cmode 1 (left/right plates): r = clamp(u + off, 0, H-1),   c = v
+//     y' = yr*r + yc*c + y0,  x' = xr*r + xc*c + x0
+// Exactly one of yr, yc is +-1: `drive` tells whether the source ROW is a function of u (0) or
+// of v (1), so the destination elements fed by a band of source rows form a sub-rectangle.
+struct PushEntry {
+  int32_t dface, oy0, ox0, U, V;
+  int32_t cmode, off;
+  int32_t yr, yc, y0, xr, xc, x0;
+  int32_t drive, L, I, doff;   // driving index i: w = clamp(i + doff, 0, L-1), i in [0, I)
+};
+
 struct CubePadGeom {
   int32_t H, W, pl, pr, pt, pd, Ho, Wo;
   int32_t corner_uses_lr[4];   // [tl, tr, dl, dr]: 1 -> corner repeats the l/r plate row, 0 -> t/d plate column
   PlateMap plate[4][6];
+  PushEntry push[6][4];
 };
 
 // rows: what the reference slices for each face, written as (face', y(r,c), x(r,c)).
@@ -97,6 +115,38 @@ inline bool make_geom(int H, int W, int pl, int pr, int pt, int pd, CubePadGeom*
   g->corner_uses_lr[1] = pt > pr;
   g->corner_uses_lr[2] = pd > pl;
   g->corner_uses_lr[3] = pd > pr;
+  // push table
+  int n_push[6] = {0, 0, 0, 0, 0, 0};
+  const AffineSrc* tables[4] = {top, down, left, right};
+  const int* cl = g->corner_uses_lr;
+  for (int P = 0; P < 4; ++P)
+    for (int f = 0; f < 6; ++f) {
+      const AffineSrc& a = tables[P][f];
+      if (n_push[a.face] >= 4) return false;   // cannot happen: every face feeds exactly 4 plates
+      PushEntry& e = g->push[a.face][n_push[a.face]++];
+      e.dface = f;
+      e.yr = a.yr; e.yc = a.yc; e.y0 = a.y0; e.xr = a.xr; e.xc = a.xc; e.x0 = a.x0;
+      if (P == P_TOP || P == P_DOWN) {
+        const int k0 = P == P_TOP ? 0 : 2;                 // corners [tl,tr] or [dl,dr]
+        const int xa = cl[k0] ? pl : 0, xb = cl[k0 + 1] ? pl + W : g->Wo;
+        e.oy0 = P == P_TOP ? 0 : pt + H; e.U = P == P_TOP ? pt : pd;
+        e.ox0 = xa; e.V = xb - xa;
+        e.cmode = 0; e.off = xa - pl;
+      } else {
+        const int kt = P == P_LEFT ? 0 : 1, kd = kt + 2;   // corners [tl,dl] or [tr,dr]
+        const int ya = cl[kt] ? 0 : pt, yb = cl[kd] ? g->Ho : pt + H;
+        e.ox0 = P == P_LEFT ? 0 : pl + W; e.V = P == P_LEFT ? pl : pr;
+        e.oy0 = ya; e.U = yb - ya;
+        e.cmode = 1; e.off = ya - pt;
+      }
+      e.drive = a.yr != 0 ? 0 : 1;
+      e.I = e.drive == 0 ? e.U : e.V;
+      const bool clamped = (e.drive == 0) == (e.cmode == 1);
+      e.L = clamped ? (e.cmode == 1 ? H : W) : e.I;
+      e.doff = clamped ? e.off : 0;
+    }
+  for (int f = 0; f < 6; ++f)
+    if (n_push[f] != 4) return false;
   return true;
 }
 

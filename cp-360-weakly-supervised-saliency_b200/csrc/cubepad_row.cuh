@@ -1,9 +1,9 @@
 // CubePad row kernel (32-bit elements) — included by cubepad.cu.
 //
-// Work unit ("tile"): a band of consecutive output rows of ONE plane, or k whole planes when
-// planes are small. Either way the input rows it copies are one contiguous, 16 B-alignable range
-// of the NCHW tensor, fetched by ONE TMA bulk load, and every input element is read from DRAM
-// exactly once.
+// Tile: a band of consecutive rows of ONE input plane, or k whole planes when planes are small.
+// Either way it is one contiguous, 16 B-alignable range of the NCHW tensor, fetched by ONE TMA
+// bulk load, and every input element is read from DRAM exactly once. A warp walks units of `ub`
+// consecutive bands of a plane so that per-plane bookkeeping is paid once per unit.
 //
 // Every warp is its own pipeline: a private ring of `slots` shared-memory buffers with one
 // mbarrier each. Lane 0 keeps `slots` bulk loads in flight; when a tile has landed the warp
@@ -12,9 +12,12 @@
 // output pitch is why the store side cannot be a tensor map — and immediately re-arms the slot
 // with the tile `slots` steps ahead. There is no __syncthreads, no producer/consumer handshake
 // and no cross-warp dependency anywhere in the steady state.
-// The few elements that are not a straight copy (side columns, top/bottom pad rows, corners) are
-// gathered from L2 through the affine plate table; their loads are issued BEFORE the warp waits
-// for its tile and consumed after the rows are copied, so their latency hides behind the copy.
+// Halo elements are PUSHED, not gathered: every halo pixel of the padded tensor is a copy of an
+// interior pixel of a neighbouring face, so while a band of face f sits in shared memory the warp
+// also writes the halo elements of the (up to four) plates of other faces that are fed by those
+// rows (cubepad_geom.h: push table, the plate maps seen from the source side; corners ride along
+// as clamped plate coordinates). The kernel therefore issues no global loads besides the bulk
+// copies: DRAM traffic is exactly one read of the input and one write of the output.
 // Integer divisions by run-time constants use host-computed multiply-shift pairs.
 #pragma once
 #include "common.cuh"
@@ -22,6 +25,12 @@
 #include "tma.cuh"
 
 namespace cp360 {
+
+#ifdef CP360_ROW_ST_DEFAULT
+#define CP360_ROW_ST(ptr, v) (*(ptr) = (v))
+#else
+#define CP360_ROW_ST(ptr, v) __stcs((ptr), (v))   // streaming store: the output is not re-read here
+#endif
 
 constexpr int kRowWarps = 8;
 constexpr int kRowThreads = kRowWarps * 32;
@@ -50,62 +59,64 @@ struct RowArgs {
   uint32_t* y;
   int64_t total_in_words;   // n_planes * H * W
   int32_t n_planes;
-  int32_t n_tiles;
+  int32_t n_units;
   int32_t C;
-  int32_t nb;               // bands per plane (1 when a tile is k whole planes)
-  int32_t Rb;               // output rows per band
-  int32_t k;                // planes per tile (1 when nb > 1)
+  int32_t Rb;               // interior rows per band
+  int32_t nb;               // bands per plane           (1 when a tile is k whole planes)
+  int32_t ub;               // bands per unit: a warp walks `ub` consecutive bands of one plane
+  int32_t upp;              // units per plane = ceil(nb / ub)
+  int32_t k;                // planes per tile           (1 when nb > 1)
   int32_t slot_words;       // capacity of one ring slot
   int32_t slots;
-  int32_t any_corner_lr;    // some corner repeats the l/r plate (asymmetric pads only)
-  FastDiv d_nb, d_C, d_nside, d_Wo;
+  int32_t ring_off;         // byte offset of the rings inside dynamic shared memory
+  FastDiv d_upp, d_C;
 };
 
-struct RowTile {
-  int32_t p0, np;           // planes [p0, p0 + np)
-  int32_t oyA, oyB;         // output rows [oyA, oyB) of each of them
-  int32_t ya, yb;           // interior input rows [ya, yb)
-  int32_t shift;            // word offset of row ya inside the slot
-  int32_t words;            // words to load (multiple of 4; 0 = nothing to copy)
-  int64_t w0;               // first word to load (multiple of 4)
+// Position of a warp in its stream of tiles: unit u (stride = number of warps in the grid),
+// tile i of the unit. Two cursors run over the same stream: the consumer and, `slots` tiles
+// ahead of it, the prefetcher.
+struct RowCursor {
+  int32_t u, i, nt;         // unit, tile in unit, tiles in unit (0: stream exhausted)
+  int32_t plane, band;      // first plane of the tile; band index inside the plane
 };
 
-__device__ __forceinline__ RowTile row_tile(const RowArgs& a, const CubePadGeom& g, int t) {
-  RowTile d;
+__device__ __forceinline__ void cursor_seek(RowCursor& cu, const RowArgs& a, int u) {
+  cu.u = u;
+  cu.i = 0;
+  if (u >= a.n_units) { cu.nt = 0; cu.plane = 0; cu.band = 0; return; }
   if (a.nb > 1) {
-    d.p0 = fdiv(t, a.d_nb);
-    const int b = t - d.p0 * a.nb;
-    d.np = 1;
-    d.oyA = b * a.Rb;
-    d.oyB = min(d.oyA + a.Rb, g.Ho);
+    cu.plane = fdiv(u, a.d_upp);
+    // skew the unit order by the plane index: a warp's stride is often a multiple of upp, and
+    // without the skew it would sit on the same band position (first / last bands carry the
+    // plate-row pushes) for the whole launch
+    int slot = u - cu.plane * a.upp + (cu.plane - fdiv(cu.plane, a.d_upp) * a.upp);
+    if (slot >= a.upp) slot -= a.upp;
+    cu.band = slot * a.ub;
+    cu.nt = min(a.ub, a.nb - cu.band);
   } else {
-    d.p0 = t * a.k;
-    d.np = min(a.k, a.n_planes - d.p0);
-    d.oyA = 0;
-    d.oyB = g.Ho;
+    cu.plane = u * a.k;
+    cu.band = 0;
+    cu.nt = 1;
   }
-  d.ya = min(max(d.oyA - g.pt, 0), g.H);
-  d.yb = min(max(d.oyB - g.pt, 0), g.H);
-  const int HW = g.H * g.W;
-  const int64_t s0 = (int64_t)d.p0 * HW + d.ya * g.W;
-  const int64_t s1 = (int64_t)(d.p0 + d.np - 1) * HW + d.yb * g.W;
-  d.w0 = s0 & ~(int64_t)3;
-  const int64_t w1 = min((s1 + 3) & ~(int64_t)3, a.total_in_words);
-  d.shift = (int)(s0 - d.w0);
-  d.words = s1 > s0 ? (int)(w1 - d.w0) : 0;
-  return d;
 }
 
-// Source of a top / bottom pad-row element (incl. corners).
-__device__ __forceinline__ int row_pad_src(const RowArgs& a, const CubePadGeom& g, int f, int oy,
-                                           int ox, int* sf) {
-  if (a.any_corner_lr) return cubepad_src(g, f, oy, ox, sf);
-  const bool top = oy < g.pt;
-  const PlateMap& m = g.plate[top ? P_TOP : P_DOWN][f];
-  const int r = top ? oy : oy - g.pt - g.H;
-  const int cc = min(max(ox - g.pl, 0), g.W - 1);      // corners repeat the plate's edge column
-  *sf = m.face;
-  return m.base + m.sr * r + m.sc * cc;
+__device__ __forceinline__ void cursor_next(RowCursor& cu, const RowArgs& a, int stride) {
+  if (++cu.i < cu.nt) ++cu.band;
+  else cursor_seek(cu, a, cu.u + stride);
+}
+
+// Destination sub-rectangle of push entry `pe` fed by source rows [ya, yb): extent `wd` of the
+// driving index starting at `i0` (the other index spans its full range). Packed i0 | wd << 16.
+__device__ __forceinline__ uint32_t push_range(const PushEntry& pe, int ya, int yb) {
+  const int sgn = pe.drive == 0 ? pe.yr : pe.yc;
+  int wa = sgn > 0 ? ya - pe.y0 : pe.y0 - yb + 1;
+  int wb = sgn > 0 ? yb - pe.y0 : pe.y0 - ya + 1;
+  wa = max(wa, 0);
+  wb = min(wb, pe.L);
+  const int i0 = wa == 0 ? 0 : wa - pe.doff;
+  const int i1 = wb == pe.L ? pe.I : wb - pe.doff;
+  const int wd = wa < wb ? i1 - i0 : 0;
+  return (uint32_t)i0 | ((uint32_t)wd << 16);
 }
 
 // nr rows of W words: sp (shared, row pitch W) -> dp (global, row pitch Wo); both already
@@ -115,7 +126,7 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
                                          int nr, int W, int Wo, int lane) {
   if (NJ == 0) {
     for (int r = 0; r < nr; ++r, sp += W, dp += Wo)
-      for (int jj = 0; jj + lane < W; jj += 32) __stcs(dp + jj, sp[jj]);
+      for (int jj = 0; jj + lane < W; jj += 32) CP360_ROW_ST(dp + jj, sp[jj]);
     return;
   }
   constexpr int NJc = NJ > 0 ? NJ : 1;
@@ -130,7 +141,7 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
         if (j < NJc - 1 || tail_ok) v[j] = sp[j * 32];
 #pragma unroll
       for (int j = 0; j < NJc; ++j)
-        if (j < NJc - 1 || tail_ok) __stcs(dp + j * 32, v[j]);
+        if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + j * 32, v[j]);
     }
   } else {
     // narrow rows: four rows per step
@@ -147,13 +158,13 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int j = 0; j < NJc; ++j)
-          if (j < NJc - 1 || tail_ok) __stcs(dp + k * Wo + j * 32, v[k][j]);
+          if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + k * Wo + j * 32, v[k][j]);
     }
 #pragma unroll 1
     for (; r < nr; ++r, sp += W, dp += Wo) {
 #pragma unroll
       for (int j = 0; j < NJc; ++j)
-        if (j < NJc - 1 || tail_ok) __stcs(dp + j * 32, sp[j * 32]);
+        if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + j * 32, sp[j * 32]);
     }
   }
 }
@@ -164,97 +175,137 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp * kRowMaxSlots;
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + kRowBarBytes) +
+  uint4* ptab = reinterpret_cast<uint4*>(smem_raw + kRowBarBytes);          // [6][nb] x 4 entries
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + a.ring_off) +
                    (size_t)warp * a.slots * a.slot_words;
-  const int H = g.H, W = g.W, Ho = g.Ho, Wo = g.Wo, HW = H * W, HoWo = Ho * Wo;
+  const int H = g.H, W = g.W, Wo = g.Wo, HW = H * W, HoWo = g.Ho * Wo;
   const int slots = a.slots;
   const int gw = blockIdx.x * kRowWarps + warp, GW = gridDim.x * kRowWarps;
-  const int64_t face_stride = (int64_t)a.C * HW;
-  const int nside = g.pl + g.pr;
 
-  auto issue = [&](int t, int s) {
-    const RowTile d = row_tile(a, g, t);
-    tma::mbar_expect_tx(&bar[s], (uint32_t)d.words * 4u);
-    if (d.words) tma::bulk_load(ring + s * a.slot_words, a.x + d.w0, (uint32_t)d.words * 4u, &bar[s]);
+  // input word range [s0, s1) of the tile under a cursor
+  auto tile_words = [&](const RowCursor& cu, int64_t* s0, int64_t* s1) {
+    if (a.nb > 1) {
+      const int ya = cu.band * a.Rb, yb = min(ya + a.Rb, H);
+      *s0 = (int64_t)cu.plane * HW + ya * W;
+      *s1 = (int64_t)cu.plane * HW + yb * W;
+    } else {
+      *s0 = (int64_t)cu.plane * HW;
+      *s1 = (int64_t)min(cu.plane + a.k, a.n_planes) * HW;
+    }
+  };
+  auto issue = [&](const RowCursor& cu, int s) {       // lane 0 only
+    int64_t s0, s1;
+    tile_words(cu, &s0, &s1);
+    const int64_t w0 = s0 & ~(int64_t)3;
+    const int64_t w1 = min((s1 + 3) & ~(int64_t)3, a.total_in_words);
+    const uint32_t bytes = (uint32_t)(w1 - w0) * 4u;
+    tma::mbar_expect_tx(&bar[s], bytes);
+    tma::bulk_load(ring + s * a.slot_words, a.x + w0, bytes, &bar[s]);
   };
 
+  // push ranges of every (face, band): computed once per CTA, one LDS.128 per tile afterwards
+  for (int i = threadIdx.x; i < 6 * a.nb * 4; i += kRowThreads) {
+    const int e = i & 3, fb = i >> 2, ff = fb / a.nb, b = fb - ff * a.nb;
+    const int ya = a.nb > 1 ? b * a.Rb : 0, yb = a.nb > 1 ? min(ya + a.Rb, H) : H;
+    reinterpret_cast<uint32_t*>(ptab)[i] = push_range(g.push[ff][e], ya, yb);
+  }
+  __syncthreads();                                     // the only block-wide sync of the kernel
+
+  RowCursor cur, pf;                                   // consumer / prefetcher
+  cursor_seek(cur, a, gw);
+  pf = cur;
   if (lane == 0) {
     for (int s = 0; s < slots; ++s) tma::mbar_init(&bar[s], 1);
     tma::fence_mbar_init();
-    int t = gw;
-    for (int s = 0; s < slots && t < a.n_tiles; ++s, t += GW) issue(t, s);
   }
   __syncwarp();
+  for (int s = 0; s < slots && pf.nt; ++s) {
+    if (lane == 0) issue(pf, s);
+    cursor_next(pf, a, GW);
+  }
 
   int s = 0;
   uint32_t phase = 0;
+  int nf = 0, c = 0, f = 0;                            // face / channel of the current plane
 #pragma unroll 1
-  for (int t = gw; t < a.n_tiles; t += GW) {
-    const RowTile d = row_tile(a, g, t);
-    const uint32_t* in_s = ring + s * a.slot_words + d.shift;
-    int nf = fdiv(d.p0, a.d_C), c = d.p0 - nf * a.C, f = nf % 6;
-    const int ntop = max(min(d.oyB, g.pt) - d.oyA, 0);
-    const int bot0 = max(d.oyA, g.pt + H), nbot = max(d.oyB - bot0, 0);
-    const int n_side = (d.yb - d.ya) * nside, n_pad = (ntop + nbot) * Wo;
-
-    const int n_halo = n_side + n_pad;
-    bool landed = false;
+  while (cur.nt) {
+    if (cur.i == 0) {                                  // new unit: locate its first plane
+      nf = fdiv(cur.plane, a.d_C);
+      c = cur.plane - nf * a.C;
+      f = nf % 6;
+    }
+    int ya, yb, np;
+    if (a.nb > 1) { ya = cur.band * a.Rb; yb = min(ya + a.Rb, H); np = 1; }
+    else { ya = 0; yb = H; np = min(a.k, a.n_planes - cur.plane); }
+    const uint32_t* in_s = ring + s * a.slot_words + (int)(((int64_t)cur.plane * HW + ya * W) & 3);
+    tma::mbar_wait(&bar[s], phase);
 #pragma unroll 1
-    for (int j = 0; j < d.np; ++j) {
-      const uint32_t* __restrict__ cube = a.x + ((int64_t)(nf - f) * a.C + c) * HW;
-      uint32_t* __restrict__ outp = a.y + (int64_t)(d.p0 + j) * HoWo;
+    for (int j = 0; j < np; ++j) {
+      const uint32_t* band = in_s + j * HW;                           // row ya of this plane
+      uint32_t* __restrict__ outp = a.y + (int64_t)(cur.plane + j) * HoWo;
 
-      // ---- A. everything that is not a straight row copy — side columns of the interior rows,
-      //         then the top / bottom pad rows incl. corners — as one list, four gathers per lane
-      //         in flight. The first batch is issued before the tile is awaited and stored after
-      //         its rows are copied.
-      uint32_t hv[4];
-      int ho[4];
-      auto gather = [&](int q0) {
+      // ---- A. interior rows: shifted copy shared -> global
+      row_copy<NJ, FULL>(band + lane, outp + (ya + g.pt) * Wo + g.pl + lane, yb - ya, W, Wo, lane);
+
+      // ---- B. push: halo elements of other faces' planes (same cube, same channel) whose source
+      //         pixel lies in rows [ya, yb) of this plane
+      int ia[4], wd[4], cnt[4];
+      const uint4 pr4 = ptab[f * a.nb + (a.nb > 1 ? cur.band : 0)];
+      const uint32_t prs[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = q0 + u * 32 + lane;
-          ho[u] = -1;
-          if (q < n_side) {
-            const int i = fdiv(q, a.d_nside), sc = q - i * nside, y = d.ya + i;
-            const bool left = sc < g.pl;
-            const PlateMap& m = g.plate[left ? P_LEFT : P_RIGHT][f];
-            const int pix = m.base + m.sr * y + m.sc * (left ? sc : sc - g.pl);
-            hv[u] = __ldg(cube + m.face * face_stride + pix);
-            ho[u] = (y + g.pt) * Wo + (left ? sc : W + sc);
-          } else if (q < n_halo) {
-            const int qp = q - n_side;
-            const int rr = fdiv(qp, a.d_Wo), ox = qp - rr * Wo;
-            const int oy = rr < ntop ? d.oyA + rr : bot0 + (rr - ntop);
-            int sf;
-            const int pix = row_pad_src(a, g, f, oy, ox, &sf);
-            hv[u] = __ldg(cube + sf * face_stride + pix);
-            ho[u] = oy * Wo + ox;
+      for (int e = 0; e < 4; ++e) {
+        const PushEntry& pe = g.push[f][e];
+        const int i0 = (int)(prs[e] & 0xffffu);
+        ia[e] = i0;
+        wd[e] = (int)(prs[e] >> 16);
+        cnt[e] = wd[e] * (pe.drive == 0 ? pe.V : pe.U);
+        if (pe.drive == 0 && pe.V >= 16 && wd[e] > 0) {
+          // whole plate rows (top / down plates fed by the first / last rows of a face): a row
+          // copy with an optional reversal and clamped ends, lanes along the row
+          uint32_t* __restrict__ dface = a.y + ((int64_t)(nf - f + pe.dface) * a.C + c) * HoWo;
+#pragma unroll 1
+          for (int u = i0; u < i0 + wd[e]; ++u) {
+            const int r = pe.cmode ? min(max(u + pe.off, 0), H - 1) : u;
+            const uint32_t* srow = band + (pe.yr * r + pe.y0 - ya) * W + pe.xr * r + pe.x0;
+            uint32_t* __restrict__ drow = dface + (pe.oy0 + u) * Wo + pe.ox0;
+#pragma unroll 1
+            for (int v = lane; v < pe.V; v += 32) {
+              const int cc = pe.cmode ? v : min(max(v + pe.off, 0), W - 1);
+              CP360_ROW_ST(drow + v, srow[pe.xc * cc]);
+            }
           }
-        }
-      };
-      auto flush = [&]() {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (ho[u] >= 0) __stcs(outp + ho[u], hv[u]);
-      };
-      gather(0);
-      // ---- B. interior rows: shifted copy shared -> global
-      if (!landed) { tma::mbar_wait(&bar[s], phase); landed = true; }
-      row_copy<NJ, FULL>(in_s + j * HW + lane, outp + (d.ya + g.pt) * Wo + g.pl + lane, d.yb - d.ya, W, Wo,
-                         lane);
-      if (j == d.np - 1) {
-        __syncwarp();                              // every lane is done reading slot s:
-        if (lane == 0) {                           // re-arm it with the tile `slots` steps ahead
-          const int tn = t + slots * GW;
-          if (tn < a.n_tiles) issue(tn, s);
+          cnt[e] = 0;
         }
       }
-      flush();
+      const int c1 = cnt[0], c2 = c1 + cnt[1], c3 = c2 + cnt[2], n_push = c3 + cnt[3];
+      uint32_t* __restrict__ cube_out = a.y + ((int64_t)(nf - f) * a.C + c) * HoWo;
 #pragma unroll 1
-      for (int q0 = 128; q0 < n_halo; q0 += 128) { gather(q0); flush(); }
-      if (++c == a.C) { c = 0; ++nf; if (++f == 6) f = 0; }
+      for (int q = lane; q < n_push; q += 32) {
+        const int e = (q >= c1) + (q >= c2) + (q >= c3);
+        const int ql = q - (e == 0 ? 0 : e == 1 ? c1 : e == 2 ? c2 : c3);
+        const int i0 = e == 0 ? ia[0] : e == 1 ? ia[1] : e == 2 ? ia[2] : ia[3];
+        const int w = e == 0 ? wd[0] : e == 1 ? wd[1] : e == 2 ? wd[2] : wd[3];
+        const PushEntry& pe = g.push[f][e];
+        // ql = t2 * den + rem; all values are far below 2^22, so the float quotient is exact
+        const int den = pe.drive == 0 ? pe.V : w;
+        const int t2 = (int)__fdividef((float)ql + 0.5f, (float)den);
+        const int rem = ql - t2 * den;
+        const int u = pe.drive == 0 ? i0 + t2 : t2;
+        const int v = pe.drive == 0 ? rem : i0 + rem;
+        const int r = pe.cmode ? min(max(u + pe.off, 0), H - 1) : u;
+        const int cc = pe.cmode ? v : min(max(v + pe.off, 0), W - 1);
+        const int yy = pe.yr * r + pe.yc * cc + pe.y0, xx = pe.xr * r + pe.xc * cc + pe.x0;
+        CP360_ROW_ST(cube_out + (int64_t)pe.dface * a.C * HoWo + (pe.oy0 + u) * Wo + pe.ox0 + v,
+                     band[(yy - ya) * W + xx]);
+      }
+      if (np > 1 && ++c == a.C) { c = 0; ++nf; if (++f == 6) f = 0; }
     }
+    __syncwarp();                                  // every lane is done reading slot s:
+    if (pf.nt) {                                   // re-arm it with the tile `slots` steps ahead
+      if (lane == 0) issue(pf, s);
+      cursor_next(pf, a, GW);
+    }
+    cursor_next(cur, a, GW);
     if (++s == slots) { s = 0; phase ^= 1u; }
   }
 }

@@ -65,6 +65,10 @@ def main():
                 cp360_b200.resnet50_cubepad_sites(224) + [(2000, 7, 1), (4000, 7, 1)]:
             if s not in sites:
                 sites.append(s)
+        only_sites = os.environ.get("CP360_KB_SITES", "")
+        if only_sites:
+            keep = {tuple(int(v) for v in t.split("x")) for t in only_sites.split(",")}
+            sites = [s for s in sites if (s[0], s[1]) in keep]
         for C, H, p in sites:
             n = 6 * B if (C, H) != (64, 256) else 12
             x = torch.randn(n, C, H, H, device=dev)
@@ -75,7 +79,9 @@ def main():
                 except _lib.CP360Error:
                     continue
                 auto = _lib.lib().cp360_cubepad_pick_algo(n, C, H, H, p, p, p, p, 4, 1) == algo
-                y = torch.empty(n, C, H + 2 * p, H + 2 * p, device=dev)
+                yoff = int(os.environ.get("CP360_KB_YOFF", "0")) // 4
+                ybuf = torch.empty(n * C * (H + 2 * p) * (H + 2 * p) + yoff, device=dev)
+                y = ybuf[yoff:].view(n, C, H + 2 * p, H + 2 * p)
                 st = torch.cuda.current_stream().cuda_stream
 
                 def fn():
