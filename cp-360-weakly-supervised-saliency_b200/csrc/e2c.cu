@@ -66,6 +66,70 @@ e2c_kernel(const float* __restrict__ frames, const uint32_t* __restrict__ packed
   }
 }
 
+// C == 3, 16 B-aligned rows: the six floats of a tap pair (pixels x0, x0+1) are 24 contiguous bytes
+// at a 4 B-aligned address. Six scalar loads per row make the L1 serve the same ~25 sectors six
+// times per warp (ncu: 25 sectors/request, lg_throttle); instead each lane fetches the 16 B-aligned
+// window that holds them with two (three when it starts 12 B in) 128-bit loads and picks its
+// floats with selects. Same arithmetic as e2c_kernel, bit-identical results.
+__device__ __forceinline__ float pick4(const float (&w)[12], int k, int o) {
+  return o == 0 ? w[k] : o == 1 ? w[k + 1] : o == 2 ? w[k + 2] : w[k + 3];
+}
+
+__device__ __forceinline__ void load_window(const float* p, const float* end, int o, float (&w)[12]) {
+  const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = __ldg(q);
+  const float4 b = reinterpret_cast<const float*>(q + 2) <= end ? __ldg(q + 1) : z;
+  const float4 c = (o == 3 && reinterpret_cast<const float*>(q + 3) <= end) ? __ldg(q + 2) : z;
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+}
+
+template <int LAYOUT, bool NORM>
+__global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
+e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
+               float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm) {
+  constexpr int C = 3;
+  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
+  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
+  const int f = blockIdx.y / tiles_y;
+  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
+  if (ox >= w || oy >= w) return;
+  const int ww = w * w;
+  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
+  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
+  const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
+  const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;   // BORDER_CONSTANT 0
+  const float* end = frames + B * (int64_t)Hin * Win * C;
+
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+    const float* row0 = frames + ((b * Hin + y0) * (int64_t)Win + x0) * C;
+    const int o = (int)((reinterpret_cast<uintptr_t>(row0) >> 2) & 3);   // same for row1: pitch % 16 == 0
+    float r0[12], r1[12];
+    load_window(row0, end, o, r0);
+    if (y1_ok) load_window(row0 + (int64_t)Win * C, end, o, r1);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float s00 = pick4(r0, c, o);
+      const float a01 = x1_ok ? pick4(r0, C + c, o) : 0.0f;
+      const float a10 = y1_ok ? pick4(r1, c, o) : 0.0f;
+      const float a11 = (x1_ok && y1_ok) ? pick4(r1, C + c, o) : 0.0f;
+      float v = __fmul_rn(s00, w00);
+      v = __fadd_rn(v, __fmul_rn(a01, w01));
+      v = __fadd_rn(v, __fmul_rn(a10, w10));
+      v = __fadd_rn(v, __fmul_rn(a11, w11));
+      if (NORM) v = __fdiv_rn(__fsub_rn(v, nrm.mean[c]), nrm.std[c]);   // utils/utils.py:28-33
+      if (LAYOUT == CP360_LAYOUT_NCHW)
+        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox, v);
+      else
+        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+    }
+  }
+}
+
 // any channel count (no normalisation)
 template <int LAYOUT>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
@@ -91,6 +155,118 @@ e2c_kernel_anyc(const float* __restrict__ frames, const uint32_t* __restrict__ p
       const float a01 = x1_ok ? __ldg(row0 + C + c) : 0.0f;
       const float a10 = y1_ok ? __ldg(row1 + c) : 0.0f;
       const float a11 = (x1_ok && y1_ok) ? __ldg(row1 + C + c) : 0.0f;
+      float v = __fmul_rn(a00, w00);
+      v = __fadd_rn(v, __fmul_rn(a01, w01));
+      v = __fadd_rn(v, __fmul_rn(a10, w10));
+      v = __fadd_rn(v, __fmul_rn(a11, w11));
+      if (LAYOUT == CP360_LAYOUT_NCHW)
+        faces[((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox] = v;
+      else
+        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+    }
+  }
+}
+
+// uint8 frames (what a video decoder / PIL resize hands over, dataset_feat_extractor.py:126-142):
+// pixel value = float32(u8) / denom — for denom = 255 this equals the reference's
+// float32(u8 / 255.0) for all 256 codes (tests/test_gpu_parity.py) — then the same fixed-point
+// bilinear arithmetic. The 256 quotients live in shared memory; a tap pair of a C = 3 row is six
+// contiguous bytes, fetched as three aligned words and realigned with funnel shifts. H2D traffic
+// and DRAM reads are a quarter of the fp32 path.
+template <int LAYOUT, bool NORM>
+__global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
+e2c_kernel_u8c3(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ packed,
+                float* __restrict__ faces, int64_t B, int Hin, int Win, int w, float denom,
+                NormParams nrm) {
+  constexpr int C = 3;
+  __shared__ float lut[256];
+  const int tid = threadIdx.y * kE2cTileX + threadIdx.x;
+  lut[tid] = __fdiv_rn((float)tid, denom);                 // block is 256 threads
+  __syncthreads();
+  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
+  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
+  const int f = blockIdx.y / tiles_y;
+  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
+  if (ox >= w || oy >= w) return;
+  const int ww = w * w;
+  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
+  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
+  const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
+  const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;   // BORDER_CONSTANT 0
+  const int64_t total_words = (B * (int64_t)Hin * Win * C + 3) >> 2;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(frames);
+
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+    const int64_t byte0 = ((b * Hin + y0) * (int64_t)Win + x0) * C;
+    uint32_t px[2][2];                                      // [row][0: bytes 0-3, 1: bytes 4-5]
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int64_t bb = byte0 + (int64_t)r * Win * C;
+      const int64_t wi = bb >> 2;
+      const int sh = (int)(bb & 3) * 8;
+      uint32_t a0 = 0, a1 = 0, a2 = 0;
+      if (r == 0 || y1_ok) {
+        a0 = __ldg(words + wi);
+        a1 = wi + 1 < total_words ? __ldg(words + wi + 1) : 0u;
+        a2 = (sh == 24 && wi + 2 < total_words) ? __ldg(words + wi + 2) : 0u;
+      }
+      px[r][0] = __funnelshift_r(a0, a1, sh);
+      px[r][1] = __funnelshift_r(a1, a2, sh);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t t00 = (px[0][0] >> (8 * c)) & 0xffu;
+      const uint32_t t01 = c == 0 ? (px[0][0] >> 24) : ((px[0][1] >> (8 * (c - 1))) & 0xffu);
+      const uint32_t t10 = (px[1][0] >> (8 * c)) & 0xffu;
+      const uint32_t t11 = c == 0 ? (px[1][0] >> 24) : ((px[1][1] >> (8 * (c - 1))) & 0xffu);
+      const float s00 = lut[t00];
+      const float a01 = x1_ok ? lut[t01] : 0.0f;
+      const float a10 = y1_ok ? lut[t10] : 0.0f;
+      const float a11 = (x1_ok && y1_ok) ? lut[t11] : 0.0f;
+      float v = __fmul_rn(s00, w00);
+      v = __fadd_rn(v, __fmul_rn(a01, w01));
+      v = __fadd_rn(v, __fmul_rn(a10, w10));
+      v = __fadd_rn(v, __fmul_rn(a11, w11));
+      if (NORM) v = __fdiv_rn(__fsub_rn(v, nrm.mean[c]), nrm.std[c]);
+      if (LAYOUT == CP360_LAYOUT_NCHW)
+        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox, v);
+      else
+        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+    }
+  }
+}
+
+// uint8, any channel count / alignment (byte loads)
+template <int LAYOUT>
+__global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
+e2c_kernel_u8_anyc(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ packed,
+                   float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w, float denom) {
+  __shared__ float lut[256];
+  const int tid = threadIdx.y * kE2cTileX + threadIdx.x;
+  lut[tid] = __fdiv_rn((float)tid, denom);
+  __syncthreads();
+  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
+  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
+  const int f = blockIdx.y / tiles_y;
+  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
+  if (ox >= w || oy >= w) return;
+  const int ww = w * w;
+  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
+  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
+  const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
+  const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+    const uint8_t* row0 = frames + ((b * Hin + y0) * (int64_t)Win + x0) * C;
+    const uint8_t* row1 = row0 + (int64_t)Win * C;
+    for (int c = 0; c < C; ++c) {
+      const float a00 = lut[__ldg(row0 + c)];
+      const float a01 = x1_ok ? lut[__ldg(row0 + C + c)] : 0.0f;
+      const float a10 = y1_ok ? lut[__ldg(row1 + c)] : 0.0f;
+      const float a11 = (x1_ok && y1_ok) ? lut[__ldg(row1 + C + c)] : 0.0f;
       float v = __fmul_rn(a00, w00);
       v = __fadd_rn(v, __fmul_rn(a01, w01));
       v = __fadd_rn(v, __fmul_rn(a10, w10));
@@ -150,6 +326,18 @@ extern "C" int cp360_e2c_fwd(const float* frames, const uint32_t* packed, float*
     else launch_c<CC, CP360_LAYOUT_NHWC>(norm, grid, block, st, frames, packed, faces, B, Hin,  \
                                           Win, w, nrm);                                         \
     break;
+  const bool vec_ok = C == 3 && ((uintptr_t)frames % 16) == 0 && ((int64_t)Win * C * 4) % 16 == 0;
+  if (vec_ok) {
+    if (nchw) {
+      if (norm) e2c_kernel_c3v<CP360_LAYOUT_NCHW, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+      else e2c_kernel_c3v<CP360_LAYOUT_NCHW, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+    } else {
+      if (norm) e2c_kernel_c3v<CP360_LAYOUT_NHWC, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+      else e2c_kernel_c3v<CP360_LAYOUT_NHWC, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+    }
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
   switch (C) {
     CP360_E2C_CASE(1)
     CP360_E2C_CASE(3)
@@ -161,6 +349,50 @@ extern "C" int cp360_e2c_fwd(const float* frames, const uint32_t* packed, float*
         e2c_kernel_anyc<CP360_LAYOUT_NHWC><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w);
   }
 #undef CP360_E2C_CASE
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+extern "C" int cp360_e2c_fwd_u8(const uint8_t* frames, const uint32_t* packed, float* faces, int64_t B,
+                                int Hin, int Win, int C, int w, int out_layout, float denom,
+                                const float* mean_host, const float* std_host, void* stream) {
+  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0 && Hin > 0 && Win > 0, CP360_ERR_BAD_ARG, "bad size");
+  CP360_CHECK_ARG(Hin * 2 == Win, CP360_ERR_SHAPE,
+                  "input must be 2:1 equirectangular (got %dx%d)", Win, Hin);
+  CP360_CHECK_ARG(Win <= 2047 && Hin <= 1023, CP360_ERR_RANGE, "packed map supports up to 2047x1023");
+  CP360_CHECK_ARG(out_layout == CP360_LAYOUT_NCHW || out_layout == CP360_LAYOUT_NHWC,
+                  CP360_ERR_BAD_ARG, "unknown layout %d", out_layout);
+  CP360_CHECK_ARG(denom > 0.0f, CP360_ERR_BAD_ARG, "denom must be positive");
+  const bool norm = mean_host != nullptr || std_host != nullptr;
+  CP360_CHECK_ARG(!norm || (mean_host && std_host && C == 3), CP360_ERR_BAD_ARG,
+                  "fused normalisation of uint8 frames needs mean and std and C == 3");
+  if (B == 0 || C == 0) return CP360_OK;
+  CP360_CHECK_ARG(frames && packed && faces, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG(((uintptr_t)faces % 4) == 0 && ((uintptr_t)packed % 4) == 0, CP360_ERR_ALIGN,
+                  "pointer not 4 B aligned");
+  int rc = require_device();
+  if (rc != CP360_OK) return rc;
+  NormParams nrm = {};
+  if (norm)
+    for (int c = 0; c < C; ++c) { nrm.mean[c] = mean_host[c]; nrm.std[c] = std_host[c]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
+  dim3 block(kE2cTileX, kE2cTileY);
+  dim3 grid((w + kE2cTileX - 1) / kE2cTileX, 6 * tiles_y, (unsigned)std::min<int64_t>(B, 65535));
+  const bool nchw = out_layout == CP360_LAYOUT_NCHW;
+  if (C == 3 && ((uintptr_t)frames % 4) == 0) {
+    if (nchw) {
+      if (norm) e2c_kernel_u8c3<CP360_LAYOUT_NCHW, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
+      else e2c_kernel_u8c3<CP360_LAYOUT_NCHW, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
+    } else {
+      if (norm) e2c_kernel_u8c3<CP360_LAYOUT_NHWC, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
+      else e2c_kernel_u8c3<CP360_LAYOUT_NHWC, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
+    }
+  } else {
+    CP360_CHECK_ARG(!norm, CP360_ERR_ALIGN, "fused normalisation needs 4 B-aligned uint8 frames");
+    if (nchw) e2c_kernel_u8_anyc<CP360_LAYOUT_NCHW><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w, denom);
+    else e2c_kernel_u8_anyc<CP360_LAYOUT_NHWC><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w, denom);
+  }
   CP360_LAUNCHED();
   return CP360_OK;
 }

@@ -133,7 +133,7 @@ class SphericalPipeline:
         return 1 + len(self.sites) + 2          # e2c, CubePads, -inf fill + c2e_max
 
     def step(self, frames, on_launch=None):
-        """frames [B,Hin,Win,3] fp32 on self.device -> sal [B,2fw,4fw] (buffer reused each step).
+        """frames [B,Hin,Win,3] fp32 (or uint8) on self.device -> sal [B,2fw,4fw] (buffer reused each step).
 
         on_launch(name, site_index): optional hook called before every C-ABI call and once after
         the last (bench.py uses it to drop CUDA events between kernels)."""
@@ -144,8 +144,12 @@ class SphericalPipeline:
         n = 6 * self.B
         if on_launch:
             on_launch("e2c", -1)
-        chk(lib.cp360_e2c_fwd(frames.data_ptr(), self._packed.data_ptr(), self.faces.data_ptr(), self.B,
-                              self.equi_h, self.equi_w, 3, self.cube, _lib.LAYOUT_NCHW, None, None, st))
+        if frames.dtype == torch.uint8:      # decoded video frames: converted as float32(u8)/255 on the fly
+            chk(lib.cp360_e2c_fwd_u8(frames.data_ptr(), self._packed.data_ptr(), self.faces.data_ptr(), self.B,
+                                     self.equi_h, self.equi_w, 3, self.cube, _lib.LAYOUT_NCHW, 255.0, None, None, st))
+        else:
+            chk(lib.cp360_e2c_fwd(frames.data_ptr(), self._packed.data_ptr(), self.faces.data_ptr(), self.B,
+                                  self.equi_h, self.equi_w, 3, self.cube, _lib.LAYOUT_NCHW, None, None, st))
         for i, (C, H, p) in enumerate(self.sites):
             if on_launch:
                 on_launch("cubepad", i)
@@ -182,17 +186,17 @@ class SphericalPipeline:
         return out_host
 
     def process_host(self, host_batches, out_host):
-        """Streamed end-to-end path: host_batches is a sequence of pinned [B,Hin,Win,3] fp32 host
-        tensors, out_host a pinned [len(host_batches),B,2fw,4fw] tensor. Uploads run on a copy
+        """Streamed end-to-end path: host_batches is a sequence of pinned [B,Hin,Win,3] host tensors
+        (uint8 video frames or float32), out_host a pinned [len(host_batches),B,2fw,4fw] tensor. Uploads run on a copy
         stream into two alternating device buffers while the previous batch computes; every
         batch's maps are copied back to the host. Returns after everything has landed."""
         dev = self.device
         B = host_batches[0].shape[0]
         if B != self.B:
             self.allocate(B)
-        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] != B:
-            self._stage = [torch.empty((B, self.equi_h, self.equi_w, 3), dtype=torch.float32, device=dev)
-                           for _ in range(2)]
+        dt = host_batches[0].dtype
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] != B or self._stage[0].dtype != dt:
+            self._stage = [torch.empty((B, self.equi_h, self.equi_w, 3), dtype=dt, device=dev) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=dev)
         compute = torch.cuda.current_stream(dev)
         copied = [torch.cuda.Event(), torch.cuda.Event()]

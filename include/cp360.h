@@ -127,6 +127,15 @@ CP360_API int cp360_e2c_fwd(const float* frames_dev, const uint32_t* packed_dev,
                   int64_t B, int Hin, int Win, int C, int w, int out_layout,
                   const float* mean_host, const float* std_host, void* stream);
 
+/* Device: the same resampling for uint8 frames [B,Hin,Win,C] (a decoded / resized video frame,
+ * dataset_feat_extractor.py:126-142, before its "/255.0"): pixel = float32(u8) / denom, which for
+ * denom = 255 equals the reference's float32(u8 / 255.0) for every code; then identical arithmetic,
+ * so faces are bit-identical to cp360_e2c_fwd on the converted frame. A quarter of the host->device
+ * and DRAM read traffic. Fused normalisation needs C == 3. */
+CP360_API int cp360_e2c_fwd_u8(const uint8_t* frames_dev, const uint32_t* packed_dev, float* faces_dev,
+                     int64_t B, int Hin, int Win, int C, int w, int out_layout, float denom,
+                     const float* mean_host, const float* std_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Cube2Equi — utils/cube_to_equi.py:11-66
  * ---------------------------------------------------------------------------------------- */

@@ -236,6 +236,36 @@ def test_e2c_fused_norm(dev):
     np.testing.assert_array_equal(fused.cpu().numpy(), want.astype(np.float32))
 
 
+def test_e2c_uint8_frames_bit_exact(dev):
+    """uint8 frames: float32(u8)/255 == float32(u8/255.0) for all 256 codes, then faces are
+    bit-identical to the fp32 path (and to the oracle) on the converted frame."""
+    codes = np.arange(256)
+    assert np.array_equal((codes / 255.0).astype(np.float32), codes.astype(np.float32) / np.float32(255))
+    for (w, H, W, C, B) in [(24, 96, 192, 3, 2), (32, 128, 256, 3, 1), (16, 66, 132, 3, 1), (16, 64, 128, 1, 2),
+                            (16, 64, 128, 4, 1), (20, 50, 100, 3, 3)]:
+        rng = np.random.default_rng(w + C)
+        u8 = rng.integers(0, 256, size=(B, H, W, C), dtype=np.uint8)
+        f32 = (u8 / 255.0).astype(np.float32)                    # the reference's conversion
+        e2c = cp360_b200.Equi2Cube(w, f32[0])
+        for layout in ("NCHW", "NHWC"):
+            got = e2c.to_cube_tensor(torch.from_numpy(u8).to(dev), layout=layout)
+            ref = e2c.to_cube_tensor(torch.from_numpy(f32).to(dev), layout=layout)
+            assert torch.equal(got, ref), (w, C, layout)
+        sx, sy = oe2c.fixed_maps(w, H, W)
+        got = e2c.to_cube_tensor(torch.from_numpy(u8).to(dev), layout="NHWC").cpu().numpy()
+        for b in range(B):
+            np.testing.assert_array_equal(got[6 * b:6 * b + 6], oe2c.to_cube(f32[b], sx, sy))
+    # misaligned base pointer (byte-load kernel) and fused normalisation
+    u8 = np.random.default_rng(3).integers(0, 256, size=(1 + 64 * 128 * 3,), dtype=np.uint8)
+    t = torch.from_numpy(u8).to(dev)[1:].view(1, 64, 128, 3)
+    e2c = cp360_b200.Equi2Cube(16, np.empty((64, 128, 3), np.float32))
+    ref = e2c.to_cube_tensor((t.float() / 255.0))
+    assert torch.equal(e2c.to_cube_tensor(t), ref)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    t2 = t.clone()
+    assert torch.equal(e2c.to_cube_tensor(t2, mean=mean, std=std), e2c.to_cube_tensor(t2.float() / 255.0, mean=mean, std=std))
+
+
 def test_e2c_float64_input_follows_dtype(dev):
     img = np.random.default_rng(9).random((64, 128, 3))            # float64 like dataset_feat_extractor.py:142
     faces = cp360_b200.Equi2Cube(16, img).to_cube(img)
