@@ -258,12 +258,16 @@ def test_e2c_uint8_frames_bit_exact(dev):
     # misaligned base pointer (byte-load kernel) and fused normalisation
     u8 = np.random.default_rng(3).integers(0, 256, size=(1 + 64 * 128 * 3,), dtype=np.uint8)
     t = torch.from_numpy(u8).to(dev)[1:].view(1, 64, 128, 3)
+    assert t.data_ptr() % 4 != 0
+    # NB the reference converts with numpy (u8 / 255.0); torch's CUDA scalar division multiplies by
+    # a reciprocal and is NOT the same rounding
+    f32 = torch.from_numpy((u8[1:].reshape(1, 64, 128, 3) / 255.0).astype(np.float32)).to(dev)
     e2c = cp360_b200.Equi2Cube(16, np.empty((64, 128, 3), np.float32))
-    ref = e2c.to_cube_tensor((t.float() / 255.0))
-    assert torch.equal(e2c.to_cube_tensor(t), ref)
+    assert torch.equal(e2c.to_cube_tensor(t), e2c.to_cube_tensor(f32))
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
     t2 = t.clone()
-    assert torch.equal(e2c.to_cube_tensor(t2, mean=mean, std=std), e2c.to_cube_tensor(t2.float() / 255.0, mean=mean, std=std))
+    assert t2.data_ptr() % 4 == 0
+    assert torch.equal(e2c.to_cube_tensor(t2, mean=mean, std=std), e2c.to_cube_tensor(f32, mean=mean, std=std))
 
 
 def test_e2c_float64_input_follows_dtype(dev):
