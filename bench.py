@@ -312,7 +312,7 @@ def run_b200(args, rank, world, local_rank):
                 C, H, p = pipe.sites[site]
                 algo = lib.cp360_cubepad_pick_algo(6 * B, C, H, H, p, p, p, p, 4, 1)
                 kname = {1: "cubepad_generic_kernel", 3: "cubepad_band_kernel", 4: "cubepad_cube_kernel",
-                         5: "cubepad_row_kernel"}[algo]
+                         5: "cubepad_row_kernel", 6: "cubepad_cube2_kernel"}[algo]
                 nbytes = pipe.cubepad_bytes_per_frame(pipe.sites[site]) * B
             elif name == "e2c":
                 kname, nbytes = "e2c_kernel", pipe.e2c_bytes_per_frame() * B

@@ -54,14 +54,16 @@ def build_library(force=False, verbose=False):
     if not force and is_fresh():
         return LIB_PATH
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
-    os.makedirs(LIB_DIR, exist_ok=True)
+    extra = os.environ.get("CP360_NVCC_EXTRA", "").split()
+    obj_dir = OBJ_DIR if not extra else OBJ_DIR + "_" + os.path.splitext(os.path.basename(LIB_PATH))[0]
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     jobs = []
     for src in CU_SOURCES:
-        obj = os.path.join(OBJ_DIR, src + ".o")
-        jobs.append(([nvcc] + NVCC_FLAGS + os.environ.get("CP360_NVCC_EXTRA", "").split() + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], obj))
+        obj = os.path.join(obj_dir, src + ".o")
+        jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], obj))
     for src in CPP_SOURCES:
-        obj = os.path.join(OBJ_DIR, src + ".o")
+        obj = os.path.join(obj_dir, src + ".o")
         jobs.append((["g++"] + CXX_FLAGS + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], obj))
     with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
         logs = list(ex.map(lambda j: _run(j[0]), jobs))

@@ -37,7 +37,7 @@ SIGNATURES = {
 CP360_OK = 0
 CP360_ERR_GROUP = 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-ALGO_AUTO, ALGO_GENERIC, ALGO_BAND_STG, ALGO_BAND_BULK, ALGO_CUBE, ALGO_ROW = range(6)
+ALGO_AUTO, ALGO_GENERIC, ALGO_BAND_STG, ALGO_BAND_BULK, ALGO_CUBE, ALGO_ROW, ALGO_CUBE2 = range(7)
 
 _lock = threading.Lock()
 _lib = None

@@ -39,6 +39,8 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 }
 
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     p[i] = v;
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(kC2eThreads)
 c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
            const float4* __restrict__ wts, float* __restrict__ out, int64_t B, int C, int w,
            int ch_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int P = 8 * w * w, ww = w * w;
   const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
   if (pix >= P) return;
@@ -98,6 +102,10 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
   const int b = blockIdx.x / groups, gidx = blockIdx.x - b * groups;
   const int c0 = gidx * kch, kl = min(kch, C - c0);
   const int tid = threadIdx.x;
+  CP360_TRACE_BEGIN(4)
+  pdl_trigger();
+  pdl_wait();
+  CP360_TRACE_T0(1);
   if (tid == 0) {
     tma::mbar_init(bar, 1);
     tma::fence_mbar_init();
@@ -109,6 +117,7 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
   }
   __syncthreads();
   tma::mbar_wait(bar, 0);
+  CP360_TRACE_T0(2);
   for (int pix = tid; pix < P; pix += kC2eSmallThreads) {
     const Tap t = decode_tap(__ldg(taps + pix));
     const float4 wt = __ldg(wts + pix);
@@ -135,6 +144,7 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
     }
     if (MODE == 1) atomic_max_float(out + (int64_t)b * P + pix, best);
   }
+  CP360_TRACE_T0(3);
 }
 
 __global__ void __launch_bounds__(kC2eThreads)
@@ -208,8 +218,7 @@ static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts,
     CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
     auto kern = c2e_small_kernel<MODE>;
     CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)(B * groups), kC2eSmallThreads, smem, st>>>(
-        cube, taps, reinterpret_cast<const float4*>(wts), out, (int)C, w, k, groups);
+    launch_kernel(kern, (unsigned)(B * groups), kC2eSmallThreads, smem, st, cube, taps, reinterpret_cast<const float4*>(wts), out, (int)C, w, k, groups);
     CP360_LAUNCHED();
     return CP360_OK;
   }
@@ -218,7 +227,7 @@ static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts,
   dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)((C + chb - 1) / chb),
             (unsigned)std::min<int64_t>(B, 65535));
   CP360_CHECK_ARG(grid.y <= 65535, CP360_ERR_RANGE, "too many channel chunks");
-  c2e_kernel<MODE><<<grid, kC2eThreads, 0, st>>>(cube, taps, reinterpret_cast<const float4*>(wts),
+  launch_kernel(c2e_kernel<MODE>, grid, kC2eThreads, 0, st, cube, taps, reinterpret_cast<const float4*>(wts),
                                                  out, B, (int)C, w, chb);
   CP360_LAUNCHED();
   return CP360_OK;
@@ -244,7 +253,7 @@ int cp360_c2e_max_fwd(const float* cube, const uint32_t* taps, const float* wts,
   CP360_CHECK_ARG(C > 0, CP360_ERR_BAD_ARG, "channel max over zero channels");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = B * 8 * (int64_t)w * w;
-  fill_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st>>>(sal, n, -INFINITY);
+  launch_kernel(fill_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st, sal, n, -INFINITY);
   CP360_LAUNCHED();
   return launch_c2e<1>(cube, taps, wts, sal, B, C, w, st);
 }
@@ -267,3 +276,10 @@ int cp360_c2e_bwd(const float* gequi, const uint32_t* taps, const float* wts, fl
 }
 
 }  // extern "C"
+
+#ifdef CP360_TRACE
+extern "C" __attribute__((visibility("default"))) int cp360_trace_bind_c2e(void* rec, unsigned cap, void* n) {
+  cp360::TraceBuf tb = {(cp360::TraceRec*)rec, cap, (unsigned*)n};
+  return cudaMemcpyToSymbol(cp360::g_tb, &tb, sizeof(tb)) == cudaSuccess ? 0 : CP360_ERR_CUDA;
+}
+#endif

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cp360 {
@@ -27,6 +28,14 @@ int require_device() {
     return CP360_ERR_CUDA;
   }
   return CP360_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("CP360_PDL");
+    return !(v && *v == '0');
+  }();
+  return on;
 }
 
 int sm_count() {

@@ -46,5 +46,79 @@ int require_device();
   } while (0)
 
 int sm_count();   // cached multiProcessorCount of the current device (148 on B200)
+bool pdl_enabled();   // CP360_PDL != 0 (default on)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
+// attribute may become resident while its predecessor on the stream is still draining. Every
+// forward kernel calls pdl_trigger() first (lets ITS successor be scheduled early) and
+// pdl_wait() before its first global-memory access (blocks until the predecessor grid has
+// completed and its writes are visible), so only launch latency and the smem prologue (tables,
+// barriers) overlap the predecessor's tail — stream order is otherwise intact. Every thread of
+// every CTA must pass pdl_wait() so that completion stays transitive along the stream.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- optional device-side timeline (build with -DCP360_TRACE; tools/trace_chain.py) ----------
+// One record per CTA: %globaltimer at entry, after pdl_wait(), when the first tile has landed and
+// at exit, plus the SM id — enough to see launch gaps, prologue, pipeline fill and tail spread of
+// back-to-back kernels inside a CUDA graph. Compiled out of the product build.
+#ifdef CP360_TRACE
+struct TraceRec { unsigned long long t[4]; unsigned kid, cta, smid, nctas; };
+struct TraceBuf { TraceRec* rec; unsigned cap; unsigned* n; };
+static __device__ TraceBuf g_tb;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CP360_TRACE_BEGIN(KID)                                                                   \
+  __shared__ TraceRec* s_trace;                                                                  \
+  if (threadIdx.x == 0 && threadIdx.y == 0) {                                                    \
+    TraceRec* r_ = nullptr;                                                                      \
+    if (g_tb.rec) {                                                                              \
+      const unsigned i_ = atomicAdd(g_tb.n, 1u);                                                 \
+      if (i_ < g_tb.cap) {                                                                       \
+        r_ = g_tb.rec + i_;                                                                      \
+        unsigned sm_;                                                                            \
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));                                         \
+        r_->t[0] = trace_now(); r_->t[1] = r_->t[2] = r_->t[3] = 0;                              \
+        r_->kid = (KID); r_->smid = sm_;                                                         \
+        r_->cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                \
+        r_->nctas = gridDim.x * gridDim.y * gridDim.z;                                           \
+      }                                                                                          \
+    }                                                                                            \
+    s_trace = r_;                                                                                \
+  }
+// thread (0,0) only, no block sync needed
+#define CP360_TRACE_T0(I) do { if (threadIdx.x == 0 && threadIdx.y == 0 && s_trace) s_trace->t[I] = trace_now(); } while (0)
+// any thread after a block-wide sync that followed CP360_TRACE_BEGIN: earliest (I=2) / latest (I=3) wins
+#define CP360_TRACE_MIN(I) do { if (s_trace) atomicMin(&s_trace->t[I], trace_now()); } while (0)
+#define CP360_TRACE_MAX(I) do { if (s_trace) atomicMax(&s_trace->t[I], trace_now()); } while (0)
+#define CP360_TRACE_INIT_MIN(I) do { if (threadIdx.x == 0 && threadIdx.y == 0 && s_trace) s_trace->t[I] = ~0ull; } while (0)
+#else
+#define CP360_TRACE_BEGIN(KID)
+#define CP360_TRACE_T0(I) do {} while (0)
+#define CP360_TRACE_MIN(I) do {} while (0)
+#define CP360_TRACE_MAX(I) do {} while (0)
+#define CP360_TRACE_INIT_MIN(I) do {} while (0)
+#endif
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 }  // namespace cp360

@@ -25,11 +25,12 @@
 #include "cubepad_geom.h"
 #include "tma.cuh"
 #include "cubepad_row.cuh"
+#include "cubepad_cube.cuh"
 
 namespace cp360 {
 
 enum CubePadAlgo { ALGO_AUTO = 0, ALGO_GENERIC = 1, ALGO_BAND_STG = 2, ALGO_BAND_BULK = 3, ALGO_CUBE = 4,
-                   ALGO_ROW = 5 };
+                   ALGO_ROW = 5, ALGO_CUBE2 = 6 };
 
 // ------------------------------------------------------------------------------------------
 // generic: any element type
@@ -38,6 +39,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 cubepad_generic_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n_planes, int C,
                        const __grid_constant__ CubePadGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
   const int64_t face_stride = (int64_t)C * HW;
   for (int64_t plane = blockIdx.y; plane < n_planes; plane += gridDim.y) {
@@ -107,11 +110,13 @@ cubepad_band_kernel(const BandArgs a, const __grid_constant__ CubePadGeom g) {
   const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
   const int64_t face_stride = (int64_t)a.C * HW;
 
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kBandStages; ++s) tma::mbar_init(&full[s], 1);
     tma::fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
 
   auto issue_load = [&](int64_t t, int s) {
     const BandTile b = band_tile(a, g, t);
@@ -222,6 +227,7 @@ cubepad_cube_kernel(const CubeArgs a, const __grid_constant__ CubePadGeom g) {
   uint16_t* lut_dst = lut_src + ((n_lut + 7) & ~7);
 
   const int tid = threadIdx.x;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kCubeStages; ++s) tma::mbar_init(&full[s], 1);
     tma::fence_mbar_init();
@@ -237,6 +243,7 @@ cubepad_cube_kernel(const CubeArgs a, const __grid_constant__ CubePadGeom g) {
     lut_dst[e] = (uint16_t)(f * a.k * HoWo + r);
   }
   __syncthreads();
+  pdl_wait();
 
   auto issue_load = [&](int64_t t, int s) {
     const int64_t grp = t / a.cblocks;
@@ -358,7 +365,7 @@ static int launch_generic(const void* x, void* y, int64_t n_planes, int C, const
                           cudaStream_t st) {
   const int HoWo = g.Ho * g.Wo;
   dim3 grid((unsigned)std::min(64, (HoWo + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
-  cubepad_generic_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (T*)y, n_planes, C, g);
+  launch_kernel(cubepad_generic_kernel<T>, grid, 256, 0, st, (const T*)x, (T*)y, n_planes, C, g);
   CP360_LAUNCHED();
   return CP360_OK;
 }
@@ -395,7 +402,66 @@ static int launch_cube(const void* x, void* y, int64_t n_faces, int C, const Cub
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
-  cubepad_cube_kernel<<<(unsigned)grid, kCubeThreads, smem, st>>>(a, g);
+  launch_kernel(cubepad_cube_kernel, (unsigned)grid, kCubeThreads, smem, st, a, g);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// Persistent kernels partition their work statically over one CTA per SM. Under programmatic
+// dependent launch a successor's CTAs become resident wherever room appears first, so two of them
+// could share an SM while another SM gets none; asking for more than half of the SM's shared
+// memory makes persistent CTAs (of this or any neighbouring launch) mutually exclusive per SM.
+static size_t exclusive_smem(size_t smem, int per_sm) {
+  const size_t floor_bytes = (size_t)env_int("CP360_PDL_PAD_KB", 116) * 1024;
+  return (per_sm == 1 && pdl_enabled()) ? std::max(smem, floor_bytes) : smem;
+}
+
+// Tiling of the cube-tile kernel (cubepad_cube.cuh). Returns false if it does not apply.
+static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* a, size_t* smem_out,
+                       int* per_sm_out) {
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  if (HoWo > 8191 || n_faces <= 0) return false;
+  int kq = 1;
+  while (kq <= 4 && (kq * HW) % 4) kq <<= 1;                   // 16 B granularity of the bulk copies
+  if (kq > 4 || C % kq) return false;
+  const int stage_kb = std::max(1, env_int("CP360_CUBE_STAGE_KB", 48));
+  int kmax = (stage_kb * 1024) / (6 * HW * 4);
+  kmax = std::min(kmax, C);
+  kmax -= kmax % kq;
+  if (kmax < kq) kmax = kq;
+  if ((int64_t)6 * kmax * HW > 65535) return false;            // 16-bit staged source offsets
+  const int stages = std::min(kCubeMaxStages, std::max(2, env_int("CP360_CUBE_STAGES", 3)));
+  a->C = C; a->kq = kq; a->kmax = kmax; a->qpc = C / kq; a->stages = stages;
+  a->n_quanta = (n_faces / 6) * a->qpc;
+  a->stage_words = 6 * kmax * HW;
+  a->lut_off = 128;
+  a->ring_off = (128 + 6 * HoWo * 4 + 127) & ~127;
+  const size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
+  if (smem > 220 * 1024) return false;
+  *smem_out = smem;
+  *per_sm_out = std::max(1, std::min(env_int("CP360_CUBE_CTAS", 1), (int)((224 * 1024) / (smem + 1024))));
+  return true;
+}
+
+static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const CubePadGeom& g,
+                        cudaStream_t st) {
+  Cube2Args a; size_t smem; int per_sm;
+  CP360_CHECK_ARG(cube2_plan(g, n_faces, C, &a, &smem, &per_sm), CP360_ERR_SHAPE,
+                  "cube-tile kernel does not apply to H=%d C=%d", g.H, C);
+  a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
+  smem = exclusive_smem(smem, per_sm);
+  CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_cube2_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int cons_warps = std::min(31, std::max(1, env_int("CP360_CUBE_WARPS", 16)));
+  // every CTA should own at least ~2 chunks
+  const int64_t chunks = (a.n_quanta * a.kq + a.kmax - 1) / a.kmax;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((chunks + 1) / 2, (int64_t)sm_count() * per_sm));
+  launch_kernel(cubepad_cube2_kernel, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;
 }
@@ -425,14 +491,9 @@ static int launch_band(const void* x, void* y, int64_t n_planes, int C, const Cu
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
-  kern<<<(unsigned)grid, kBandThreads, smem, st>>>(a, g);
+  launch_kernel(kern, (unsigned)grid, kBandThreads, smem, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
 }
 
 // Tiling of the row kernel. Returns false if it does not apply.
@@ -450,6 +511,19 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
     int rb = std::max(1, (target_words + target_words / 8) / g.W);
     if (g.W < 128) rb = std::max(4, (target_words + target_words / 4) / g.W / 4 * 4);   // narrow rows: copied four at a time
     if (rb_env > 0) rb = rb_env;
+    else if (env_int("CP360_ROW_BALANCE", 1)) {
+      // near-equal bands: a short last band pays the full per-tile cost for a fraction of the bytes
+      const int nb0 = (g.H + rb - 1) / rb;
+      int best_rb = rb, best_cost = 1 << 30;
+      for (int nbc = std::max(1, nb0 - 1); nbc <= nb0 + 2; ++nbc) {
+        const int r = (g.H + nbc - 1) / nbc;
+        const int n = (g.H + r - 1) / r;
+        int cost = 8 * (n * r - g.H) + std::abs(r - rb);       // rows missing in the last band, then distance
+        if (g.W < 128 && r % 4) cost += 2;                     // narrow rows are copied four at a time
+        if (cost < best_cost) { best_cost = cost; best_rb = r; }
+      }
+      rb = best_rb;
+    }
     a->Rb = rb;
     while ((g.H + rb - 1) / rb > 256) ++rb;                    // push-range table: 6 * nb * 16 B of shared memory
     a->nb = (g.H + rb - 1) / rb;
@@ -471,6 +545,8 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
     a->n_units = (int32_t)((n_planes + a->k - 1) / a->k);
   }
   a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 3)));
+  a->stagger_ns = env_int("CP360_ROW_STAGGER_NS", 0);
+  a->order = env_int("CP360_ROW_ORDER", 0);
   a->d_upp = make_fastdiv((uint32_t)a->upp);
   a->d_C = make_fastdiv((uint32_t)C);
   return true;
@@ -499,12 +575,13 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
     case 8: if (full) kern = cubepad_row_kernel<8, true>; break;
     default: break;
   }
-  CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = std::max(1, std::min(2048 / kRowThreads, (int)((224 * 1024) / (smem + 1024))));
   per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 1)));
+  const size_t smem_req = exclusive_smem(smem, per_sm);
+  CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
   const int64_t ctas_needed = ((int64_t)a.n_units + kRowWarps - 1) / kRowWarps;
   const int64_t grid = std::min<int64_t>(ctas_needed, (int64_t)sm_count() * per_sm);
-  kern<<<(unsigned)grid, kRowThreads, smem, st>>>(a, g);
+  launch_kernel(kern, (unsigned)grid, kRowThreads, smem_req, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;
 }
@@ -525,7 +602,10 @@ static int validate(const void* x, void* y, int64_t n_faces, int64_t C, int H, i
 }
 
 static int pick_algo(const CubePadGeom& g, int64_t n_faces, int C, bool fast_ok) {
-  int k; size_t smem; RowArgs ra;
+  int k; size_t smem; RowArgs ra; Cube2Args ca; int per_sm;
+  const int cube_max_h = env_int("CP360_CUBE_MAX_H", 23);
+  if (fast_ok && g.H <= cube_max_h && env_int("CP360_CUBE_ALGO", ALGO_CUBE2) == ALGO_CUBE2 &&
+      cube2_plan(g, n_faces, C, &ca, &smem, &per_sm)) return ALGO_CUBE2;
   if (fast_ok && g.H >= 24 && row_plan(g, n_faces * C, C, &ra)) return ALGO_ROW;
   if (fast_ok && g.H <= 32 && cube_plan(g, C, &k, &smem)) return ALGO_CUBE;
   if (fast_ok && g.H >= 24 && band_ok(g)) return ALGO_BAND_BULK;
@@ -594,6 +674,9 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
     case ALGO_CUBE:
       CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "cube-tile kernel needs 4-byte elements, 16 B aligned");
       return launch_cube(x, y, n_faces, (int)C, g, st);
+    case ALGO_CUBE2:
+      CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "cube-tile kernel needs 4-byte elements, 16 B aligned");
+      return launch_cube2(x, y, n_faces, (int)C, g, st);
     case ALGO_BAND_STG:
     case ALGO_BAND_BULK:
       CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "band kernel needs 4-byte elements, 16 B aligned");
@@ -643,3 +726,10 @@ int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C
 }
 
 }  // extern "C"
+
+#ifdef CP360_TRACE
+extern "C" __attribute__((visibility("default"))) int cp360_trace_bind_cubepad(void* rec, unsigned cap, void* n) {
+  cp360::TraceBuf tb = {(cp360::TraceRec*)rec, cap, (unsigned*)n};
+  return cudaMemcpyToSymbol(cp360::g_tb, &tb, sizeof(tb)) == cudaSuccess ? 0 : CP360_ERR_CUDA;
+}
+#endif

@@ -69,6 +69,8 @@ struct RowArgs {
   int32_t slot_words;       // capacity of one ring slot
   int32_t slots;
   int32_t ring_off;         // byte offset of the rings inside dynamic shared memory
+  int32_t stagger_ns;       // experiment knob: warp w starts (w % 8) * stagger_ns late (0 = off)
+  int32_t order;            // 0: units dealt round-robin to the grid's warps; 1: one contiguous range per warp
   FastDiv d_upp, d_C;
 };
 
@@ -77,20 +79,24 @@ struct RowArgs {
 // ahead of it, the prefetcher.
 struct RowCursor {
   int32_t u, i, nt;         // unit, tile in unit, tiles in unit (0: stream exhausted)
+  int32_t u_end;            // end of this warp's units
   int32_t plane, band;      // first plane of the tile; band index inside the plane
 };
 
 __device__ __forceinline__ void cursor_seek(RowCursor& cu, const RowArgs& a, int u) {
   cu.u = u;
   cu.i = 0;
-  if (u >= a.n_units) { cu.nt = 0; cu.plane = 0; cu.band = 0; return; }
+  if (u >= cu.u_end) { cu.nt = 0; cu.plane = 0; cu.band = 0; return; }
   if (a.nb > 1) {
     cu.plane = fdiv(u, a.d_upp);
     // skew the unit order by the plane index: a warp's stride is often a multiple of upp, and
     // without the skew it would sit on the same band position (first / last bands carry the
     // plate-row pushes) for the whole launch
-    int slot = u - cu.plane * a.upp + (cu.plane - fdiv(cu.plane, a.d_upp) * a.upp);
-    if (slot >= a.upp) slot -= a.upp;
+    int slot = u - cu.plane * a.upp;
+    if (a.order == 0) {
+      slot += cu.plane - fdiv(cu.plane, a.d_upp) * a.upp;
+      if (slot >= a.upp) slot -= a.upp;
+    }
     cu.band = slot * a.ub;
     cu.nt = min(a.ub, a.nb - cu.band);
   } else {
@@ -203,6 +209,9 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     tma::bulk_load(ring + s * a.slot_words, a.x + w0, bytes, &bar[s]);
   };
 
+  CP360_TRACE_BEGIN(1)
+  pdl_trigger();
+  CP360_TRACE_INIT_MIN(2);
   // push ranges of every (face, band): computed once per CTA, one LDS.128 per tile afterwards
   for (int i = threadIdx.x; i < 6 * a.nb * 4; i += kRowThreads) {
     const int e = i & 3, fb = i >> 2, ff = fb / a.nb, b = fb - ff * a.nb;
@@ -210,9 +219,19 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     reinterpret_cast<uint32_t*>(ptab)[i] = push_range(g.push[ff][e], ya, yb);
   }
   __syncthreads();                                     // the only block-wide sync of the kernel
+  pdl_wait();
+  CP360_TRACE_T0(1);
 
+  if (a.stagger_ns > 0) __nanosleep((unsigned)((gw * 5 % 8) * a.stagger_ns));
   RowCursor cur, pf;                                   // consumer / prefetcher
-  cursor_seek(cur, a, gw);
+  int u_first = gw, u_stride = GW;
+  cur.u_end = a.n_units;
+  if (a.order == 1) {
+    u_first = (int)(((int64_t)a.n_units * gw) / GW);
+    cur.u_end = (int)(((int64_t)a.n_units * (gw + 1)) / GW);
+    u_stride = 1;
+  }
+  cursor_seek(cur, a, u_first);
   pf = cur;
   if (lane == 0) {
     for (int s = 0; s < slots; ++s) tma::mbar_init(&bar[s], 1);
@@ -221,7 +240,7 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   __syncwarp();
   for (int s = 0; s < slots && pf.nt; ++s) {
     if (lane == 0) issue(pf, s);
-    cursor_next(pf, a, GW);
+    cursor_next(pf, a, u_stride);
   }
 
   int s = 0;
@@ -239,6 +258,9 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     else { ya = 0; yb = H; np = min(a.k, a.n_planes - cur.plane); }
     const uint32_t* in_s = ring + s * a.slot_words + (int)(((int64_t)cur.plane * HW + ya * W) & 3);
     tma::mbar_wait(&bar[s], phase);
+#ifdef CP360_TRACE
+    if (lane == 0 && cur.u == u_first && cur.i == 0) CP360_TRACE_MIN(2);
+#endif
 #pragma unroll 1
     for (int j = 0; j < np; ++j) {
       const uint32_t* band = in_s + j * HW;                           // row ya of this plane
@@ -303,11 +325,14 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     __syncwarp();                                  // every lane is done reading slot s:
     if (pf.nt) {                                   // re-arm it with the tile `slots` steps ahead
       if (lane == 0) issue(pf, s);
-      cursor_next(pf, a, GW);
+      cursor_next(pf, a, u_stride);
     }
-    cursor_next(cur, a, GW);
+    cursor_next(cur, a, u_stride);
     if (++s == slots) { s = 0; phase ^= 1u; }
   }
+#ifdef CP360_TRACE
+  if (lane == 0) CP360_TRACE_MAX(3);
+#endif
 }
 
 }  // namespace cp360

@@ -28,6 +28,8 @@ template <int C, int LAYOUT, bool NORM>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
            float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm) {
+  pdl_trigger();
+  pdl_wait();
   const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
   const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
   const int f = blockIdx.y / tiles_y;
@@ -91,6 +93,10 @@ __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
                float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm) {
   constexpr int C = 3;
+  CP360_TRACE_BEGIN(3)
+  pdl_trigger();
+  pdl_wait();
+  CP360_TRACE_T0(1);
   const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
   const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
   const int f = blockIdx.y / tiles_y;
@@ -128,6 +134,7 @@ e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ pa
         faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
     }
   }
+  CP360_TRACE_T0(3);
 }
 
 // any channel count (no normalisation)
@@ -135,6 +142,8 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel_anyc(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
                 float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w) {
+  pdl_trigger();
+  pdl_wait();
   const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
   const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
   const int f = blockIdx.y / tiles_y;
@@ -181,8 +190,10 @@ e2c_kernel_u8c3(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
   constexpr int C = 3;
   __shared__ float lut[256];
   const int tid = threadIdx.y * kE2cTileX + threadIdx.x;
+  pdl_trigger();
   lut[tid] = __fdiv_rn((float)tid, denom);                 // block is 256 threads
   __syncthreads();
+  pdl_wait();
   const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
   const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
   const int f = blockIdx.y / tiles_y;
@@ -245,8 +256,10 @@ e2c_kernel_u8_anyc(const uint8_t* __restrict__ frames, const uint32_t* __restric
                    float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w, float denom) {
   __shared__ float lut[256];
   const int tid = threadIdx.y * kE2cTileX + threadIdx.x;
+  pdl_trigger();
   lut[tid] = __fdiv_rn((float)tid, denom);
   __syncthreads();
+  pdl_wait();
   const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
   const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
   const int f = blockIdx.y / tiles_y;
@@ -284,9 +297,9 @@ static void launch_c(bool norm, dim3 grid, dim3 block, cudaStream_t st, const fl
                      const uint32_t* packed, float* faces, int64_t B, int Hin, int Win, int w,
                      const NormParams& nrm) {
   if (norm)
-    e2c_kernel<C, LAYOUT, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+    launch_kernel(e2c_kernel<C, LAYOUT, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
   else
-    e2c_kernel<C, LAYOUT, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+    launch_kernel(e2c_kernel<C, LAYOUT, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
 }
 
 }  // namespace cp360
@@ -329,11 +342,11 @@ extern "C" int cp360_e2c_fwd(const float* frames, const uint32_t* packed, float*
   const bool vec_ok = C == 3 && ((uintptr_t)frames % 16) == 0 && ((int64_t)Win * C * 4) % 16 == 0;
   if (vec_ok) {
     if (nchw) {
-      if (norm) e2c_kernel_c3v<CP360_LAYOUT_NCHW, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
-      else e2c_kernel_c3v<CP360_LAYOUT_NCHW, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+      if (norm) launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NCHW, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
+      else launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NCHW, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
     } else {
-      if (norm) e2c_kernel_c3v<CP360_LAYOUT_NHWC, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
-      else e2c_kernel_c3v<CP360_LAYOUT_NHWC, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, nrm);
+      if (norm) launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NHWC, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
+      else launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NHWC, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
     }
     CP360_LAUNCHED();
     return CP360_OK;
@@ -344,9 +357,9 @@ extern "C" int cp360_e2c_fwd(const float* frames, const uint32_t* packed, float*
     CP360_E2C_CASE(4)
     default:
       if (nchw)
-        e2c_kernel_anyc<CP360_LAYOUT_NCHW><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w);
+        launch_kernel(e2c_kernel_anyc<CP360_LAYOUT_NCHW>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w);
       else
-        e2c_kernel_anyc<CP360_LAYOUT_NHWC><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w);
+        launch_kernel(e2c_kernel_anyc<CP360_LAYOUT_NHWC>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w);
   }
 #undef CP360_E2C_CASE
   CP360_LAUNCHED();
@@ -382,17 +395,24 @@ extern "C" int cp360_e2c_fwd_u8(const uint8_t* frames, const uint32_t* packed, f
   const bool nchw = out_layout == CP360_LAYOUT_NCHW;
   if (C == 3 && ((uintptr_t)frames % 4) == 0) {
     if (nchw) {
-      if (norm) e2c_kernel_u8c3<CP360_LAYOUT_NCHW, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
-      else e2c_kernel_u8c3<CP360_LAYOUT_NCHW, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
+      if (norm) launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NCHW, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
+      else launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NCHW, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
     } else {
-      if (norm) e2c_kernel_u8c3<CP360_LAYOUT_NHWC, true><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
-      else e2c_kernel_u8c3<CP360_LAYOUT_NHWC, false><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, w, denom, nrm);
+      if (norm) launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NHWC, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
+      else launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NHWC, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
     }
   } else {
     CP360_CHECK_ARG(!norm, CP360_ERR_ALIGN, "fused normalisation needs 4 B-aligned uint8 frames");
-    if (nchw) e2c_kernel_u8_anyc<CP360_LAYOUT_NCHW><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w, denom);
-    else e2c_kernel_u8_anyc<CP360_LAYOUT_NHWC><<<grid, block, 0, st>>>(frames, packed, faces, B, Hin, Win, C, w, denom);
+    if (nchw) launch_kernel(e2c_kernel_u8_anyc<CP360_LAYOUT_NCHW>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w, denom);
+    else launch_kernel(e2c_kernel_u8_anyc<CP360_LAYOUT_NHWC>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w, denom);
   }
   CP360_LAUNCHED();
   return CP360_OK;
 }
+
+#ifdef CP360_TRACE
+extern "C" __attribute__((visibility("default"))) int cp360_trace_bind_e2c(void* rec, unsigned cap, void* n) {
+  cp360::TraceBuf tb = {(cp360::TraceRec*)rec, cap, (unsigned*)n};
+  return cudaMemcpyToSymbol(cp360::g_tb, &tb, sizeof(tb)) == cudaSuccess ? 0 : CP360_ERR_CUDA;
+}
+#endif

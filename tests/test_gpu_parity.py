@@ -46,7 +46,7 @@ def gather_reference(x, imap):
 
 
 ALGOS = [_lib.ALGO_AUTO, _lib.ALGO_GENERIC, _lib.ALGO_BAND_STG, _lib.ALGO_BAND_BULK, _lib.ALGO_CUBE,
-         _lib.ALGO_ROW]
+         _lib.ALGO_ROW, _lib.ALGO_CUBE2]
 
 
 # ------------------------------------------------------------------------------------------

@@ -73,7 +73,7 @@ def main():
             n = 6 * B if (C, H) != (64, 256) else 12
             x = torch.randn(n, C, H, H, device=dev)
             nbytes = n * C * (H * H + (H + 2 * p) ** 2) * 4
-            for algo, an in ((1, "generic"), (3, "band_bulk"), (4, "cube"), (5, "row")):
+            for algo, an in ((1, "generic"), (4, "cube"), (5, "row"), (6, "cube2")):
                 try:
                     cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
                 except _lib.CP360Error:

@@ -12,12 +12,21 @@ import cp360_b200
 
 kind = sys.argv[1]
 dev = torch.device("cuda", 0)
+FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if os.environ.get("CP360_PROF_FLUSH") else None
+
+
+def flush():
+    if FLUSH is not None:
+        FLUSH.zero_()
+
+
 if kind == "cubepad":
     C, H, p = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     algo = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     B = int(sys.argv[6]) if len(sys.argv) > 6 else 16
     x = torch.randn(6 * B, C, H, H, device=dev)
-    for _ in range(3):
+    for _ in range(3 if FLUSH is None else 5):
+        flush()
         y = cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
 elif kind == "e2c":
     w = int(sys.argv[2]); B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
