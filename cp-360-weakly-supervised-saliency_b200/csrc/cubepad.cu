@@ -505,13 +505,14 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
   a->C = C;
   a->n_planes = (int32_t)n_planes;
   a->total_in_words = n_planes * HW;
-  const int rb_env = env_int("CP360_ROW_RB", 0);
+  const int rb_w = env_int("CP360_ROW_RB_W", 0);               // tuning knob: CP360_ROW_RB applies to this W only
+  const int rb_env = (rb_w == 0 || rb_w == g.W) ? env_int("CP360_ROW_RB", 0) : 0;
   if ((rb_env > 0 && rb_env < g.H) || (rb_env == 0 && HW > target_words + target_words / 2)) {   // bands of rows inside one plane
     // ~4.5 KB tiles (5 KB for narrow rows) measured best on B200; see profiles/README.md
     int rb = std::max(1, (target_words + target_words / 8) / g.W);
     if (g.W < 128) rb = std::max(4, (target_words + target_words / 4) / g.W / 4 * 4);   // narrow rows: copied four at a time
     if (rb_env > 0) rb = rb_env;
-    else if (env_int("CP360_ROW_BALANCE", 1)) {
+    else if (env_int("CP360_ROW_BALANCE", 0)) {
       // near-equal bands: a short last band pays the full per-tile cost for a fraction of the bytes
       const int nb0 = (g.H + rb - 1) / rb;
       int best_rb = rb, best_cost = 1 << 30;
@@ -528,25 +529,21 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
     while ((g.H + rb - 1) / rb > 256) ++rb;                    // push-range table: 6 * nb * 16 B of shared memory
     a->nb = (g.H + rb - 1) / rb;
     a->k = 1;
-    // a warp walks `ub` consecutive bands; keep >= ~16 units per warp for load balance
-    const int64_t warps = (int64_t)sm_count() * kRowWarps;
-    int ub = std::max(1, env_int("CP360_ROW_UNIT_BANDS", 1));
-    while (ub > 1 && n_planes * ((a->nb + ub - 1) / ub) < 16 * warps) ub >>= 1;
-    a->ub = std::min(ub, a->nb);
-    a->upp = (a->nb + a->ub - 1) / a->ub;
+    a->upp = a->nb;
     a->slot_words = ((rb * g.W + 8) + 31) & ~31;
     if (n_planes * a->upp > 0x7fffffff) return false;
     a->n_units = (int32_t)(n_planes * a->upp);
   } else {                                                     // k whole planes per tile
-    a->nb = 1; a->ub = 1; a->upp = 1;
+    a->nb = 1; a->upp = 1;
     a->Rb = g.H;
     a->k = std::max(1, target_words / HW);
     a->slot_words = ((a->k * HW + 8) + 31) & ~31;
     a->n_units = (int32_t)((n_planes + a->k - 1) / a->k);
   }
   a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 3)));
-  a->stagger_ns = env_int("CP360_ROW_STAGGER_NS", 0);
-  a->order = env_int("CP360_ROW_ORDER", 0);
+  a->order = env_int("CP360_ROW_ORDER", 2) == 2 ? 2 : 0;
+  // the dynamic order hands out k = 0, 1, 2, ... per CTA and maps it to (k / 8) * warps_in_grid + ...
+  if ((int64_t)a->n_units + (int64_t)sm_count() * kRowWarps * 16 > 0x7fffffff) return false;
   a->d_upp = make_fastdiv((uint32_t)a->upp);
   a->d_C = make_fastdiv((uint32_t)C);
   return true;

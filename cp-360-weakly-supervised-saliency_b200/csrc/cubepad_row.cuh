@@ -35,7 +35,9 @@ namespace cp360 {
 constexpr int kRowWarps = 8;
 constexpr int kRowThreads = kRowWarps * 32;
 constexpr int kRowMaxSlots = 8;
-constexpr int kRowBarBytes = kRowWarps * kRowMaxSlots * 8;
+constexpr int kRowMetaOff = kRowWarps * kRowMaxSlots * 8;            // per-slot (plane, band) of the tile in flight
+constexpr int kRowCtrOff = 2 * kRowMetaOff;                            // CTA-wide unit counter
+constexpr int kRowBarBytes = kRowCtrOff + 16;
 
 // n / d for 0 <= n < 2^31 as umulhi(n, m) >> s  (m == 0: d == 1)
 struct FastDiv { uint32_t m, s; };
@@ -63,52 +65,30 @@ struct RowArgs {
   int32_t C;
   int32_t Rb;               // interior rows per band
   int32_t nb;               // bands per plane           (1 when a tile is k whole planes)
-  int32_t ub;               // bands per unit: a warp walks `ub` consecutive bands of one plane
-  int32_t upp;              // units per plane = ceil(nb / ub)
+  int32_t upp;              // units per plane (= nb)
   int32_t k;                // planes per tile           (1 when nb > 1)
   int32_t slot_words;       // capacity of one ring slot
   int32_t slots;
   int32_t ring_off;         // byte offset of the rings inside dynamic shared memory
-  int32_t stagger_ns;       // experiment knob: warp w starts (w % 8) * stagger_ns late (0 = off)
-  int32_t order;            // 0: units dealt round-robin to the grid's warps; 1: one contiguous range per warp
+  int32_t order;            // 0: units dealt round-robin to the grid's warps (static); 2: dealt round-robin to
+                            //    CTAs in groups of 8, warps of a CTA draw from the CTA's list (dynamic)
   FastDiv d_upp, d_C;
 };
 
-// Position of a warp in its stream of tiles: unit u (stride = number of warps in the grid),
-// tile i of the unit. Two cursors run over the same stream: the consumer and, `slots` tiles
-// ahead of it, the prefetcher.
-struct RowCursor {
-  int32_t u, i, nt;         // unit, tile in unit, tiles in unit (0: stream exhausted)
-  int32_t u_end;            // end of this warp's units
-  int32_t plane, band;      // first plane of the tile; band index inside the plane
-};
-
-__device__ __forceinline__ void cursor_seek(RowCursor& cu, const RowArgs& a, int u) {
-  cu.u = u;
-  cu.i = 0;
-  if (u >= cu.u_end) { cu.nt = 0; cu.plane = 0; cu.band = 0; return; }
+// A unit is one tile: band `band` of plane `plane` (nb > 1), or k whole planes starting at `plane`.
+__device__ __forceinline__ int2 unit_decode(const RowArgs& a, int u) {
   if (a.nb > 1) {
-    cu.plane = fdiv(u, a.d_upp);
-    // skew the unit order by the plane index: a warp's stride is often a multiple of upp, and
-    // without the skew it would sit on the same band position (first / last bands carry the
-    // plate-row pushes) for the whole launch
-    int slot = u - cu.plane * a.upp;
+    const int plane = fdiv(u, a.d_upp);
+    int band = u - plane * a.upp;
     if (a.order == 0) {
-      slot += cu.plane - fdiv(cu.plane, a.d_upp) * a.upp;
-      if (slot >= a.upp) slot -= a.upp;
+      // static dealing: a warp's stride is often a multiple of upp; rotate the band order by the
+      // plane index so that no warp sits on the first / last bands (plate-row pushes) all launch
+      band += plane - fdiv(plane, a.d_upp) * a.upp;
+      if (band >= a.upp) band -= a.upp;
     }
-    cu.band = slot * a.ub;
-    cu.nt = min(a.ub, a.nb - cu.band);
-  } else {
-    cu.plane = u * a.k;
-    cu.band = 0;
-    cu.nt = 1;
+    return make_int2(plane, band);
   }
-}
-
-__device__ __forceinline__ void cursor_next(RowCursor& cu, const RowArgs& a, int stride) {
-  if (++cu.i < cu.nt) ++cu.band;
-  else cursor_seek(cu, a, cu.u + stride);
+  return make_int2(u * a.k, 0);
 }
 
 // Destination sub-rectangle of push entry `pe` fed by source rows [ya, yb): extent `wd` of the
@@ -187,31 +167,50 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   const int H = g.H, W = g.W, Wo = g.Wo, HW = H * W, HoWo = g.Ho * Wo;
   const int slots = a.slots;
   const int gw = blockIdx.x * kRowWarps + warp, GW = gridDim.x * kRowWarps;
+  int2* meta = reinterpret_cast<int2*>(smem_raw + kRowMetaOff) + warp * kRowMaxSlots;
+  int* ctr = reinterpret_cast<int*>(smem_raw + kRowCtrOff);
 
-  // input word range [s0, s1) of the tile under a cursor
-  auto tile_words = [&](const RowCursor& cu, int64_t* s0, int64_t* s1) {
-    if (a.nb > 1) {
-      const int ya = cu.band * a.Rb, yb = min(ya + a.Rb, H);
-      *s0 = (int64_t)cu.plane * HW + ya * W;
-      *s1 = (int64_t)cu.plane * HW + yb * W;
-    } else {
-      *s0 = (int64_t)cu.plane * HW;
-      *s1 = (int64_t)min(cu.plane + a.k, a.n_planes) * HW;
-    }
-  };
-  auto issue = [&](const RowCursor& cu, int s) {       // lane 0 only
+  // lane 0: bulk-load the tile (plane, band) into slot s
+  auto issue = [&](int plane, int band, int s) {
     int64_t s0, s1;
-    tile_words(cu, &s0, &s1);
+    if (a.nb > 1) {
+      const int ya = band * a.Rb, yb = min(ya + a.Rb, H);
+      s0 = (int64_t)plane * HW + ya * W;
+      s1 = (int64_t)plane * HW + yb * W;
+    } else {
+      s0 = (int64_t)plane * HW;
+      s1 = (int64_t)min(plane + a.k, a.n_planes) * HW;
+    }
     const int64_t w0 = s0 & ~(int64_t)3;
     const int64_t w1 = min((s1 + 3) & ~(int64_t)3, a.total_in_words);
     const uint32_t bytes = (uint32_t)(w1 - w0) * 4u;
     tma::mbar_expect_tx(&bar[s], bytes);
     tma::bulk_load(ring + s * a.slot_words, a.x + w0, bytes, &bar[s]);
   };
+  // lane 0: take the warp's next unit, publish it as slot s's tile and start its load
+  int my_k = 0;
+  auto arm = [&](int s) {
+    int u;
+    if (a.order == 2) {
+      const int k = atomicAdd(ctr, 1);
+      u = (k >> 3) * GW + blockIdx.x * kRowWarps + (k & 7);
+    } else {
+      u = gw + my_k * GW;
+      ++my_k;
+    }
+    if (u < a.n_units) {
+      const int2 m = unit_decode(a, u);
+      meta[s] = m;
+      issue(m.x, m.y, s);
+    } else {
+      meta[s] = make_int2(-1, 0);
+    }
+  };
 
   CP360_TRACE_BEGIN(1)
   pdl_trigger();
   CP360_TRACE_INIT_MIN(2);
+  if (threadIdx.x == 0) *ctr = 0;
   // push ranges of every (face, band): computed once per CTA, one LDS.128 per tile afterwards
   for (int i = threadIdx.x; i < 6 * a.nb * 4; i += kRowThreads) {
     const int e = i & 3, fb = i >> 2, ff = fb / a.nb, b = fb - ff * a.nb;
@@ -222,49 +221,39 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   pdl_wait();
   CP360_TRACE_T0(1);
 
-  if (a.stagger_ns > 0) __nanosleep((unsigned)((gw * 5 % 8) * a.stagger_ns));
-  RowCursor cur, pf;                                   // consumer / prefetcher
-  int u_first = gw, u_stride = GW;
-  cur.u_end = a.n_units;
-  if (a.order == 1) {
-    u_first = (int)(((int64_t)a.n_units * gw) / GW);
-    cur.u_end = (int)(((int64_t)a.n_units * (gw + 1)) / GW);
-    u_stride = 1;
-  }
-  cursor_seek(cur, a, u_first);
-  pf = cur;
   if (lane == 0) {
     for (int s = 0; s < slots; ++s) tma::mbar_init(&bar[s], 1);
     tma::fence_mbar_init();
+    for (int s = 0; s < slots; ++s) arm(s);
   }
   __syncwarp();
-  for (int s = 0; s < slots && pf.nt; ++s) {
-    if (lane == 0) issue(pf, s);
-    cursor_next(pf, a, u_stride);
-  }
 
   int s = 0;
   uint32_t phase = 0;
-  int nf = 0, c = 0, f = 0;                            // face / channel of the current plane
+#ifdef CP360_TRACE
+  bool first_tile = true;
+#endif
 #pragma unroll 1
-  while (cur.nt) {
-    if (cur.i == 0) {                                  // new unit: locate its first plane
-      nf = fdiv(cur.plane, a.d_C);
-      c = cur.plane - nf * a.C;
-      f = nf % 6;
-    }
+  while (true) {
+    const int2 m = meta[s];
+    if (m.x < 0) break;                                // units are drawn in increasing order: nothing behind it
+    const int plane0 = m.x, band_i = m.y;
+    int nf = fdiv(plane0, a.d_C);                      // face / channel of the (first) plane
+    int c = plane0 - nf * a.C;
+    int f = nf % 6;
     int ya, yb, np;
-    if (a.nb > 1) { ya = cur.band * a.Rb; yb = min(ya + a.Rb, H); np = 1; }
-    else { ya = 0; yb = H; np = min(a.k, a.n_planes - cur.plane); }
-    const uint32_t* in_s = ring + s * a.slot_words + (int)(((int64_t)cur.plane * HW + ya * W) & 3);
+    if (a.nb > 1) { ya = band_i * a.Rb; yb = min(ya + a.Rb, H); np = 1; }
+    else { ya = 0; yb = H; np = min(a.k, a.n_planes - plane0); }
+    const uint32_t* in_s = ring + s * a.slot_words + (int)(((int64_t)plane0 * HW + ya * W) & 3);
     tma::mbar_wait(&bar[s], phase);
 #ifdef CP360_TRACE
-    if (lane == 0 && cur.u == u_first && cur.i == 0) CP360_TRACE_MIN(2);
+    if (lane == 0 && first_tile) CP360_TRACE_MIN(2);
+    first_tile = false;
 #endif
 #pragma unroll 1
     for (int j = 0; j < np; ++j) {
       const uint32_t* band = in_s + j * HW;                           // row ya of this plane
-      uint32_t* __restrict__ outp = a.y + (int64_t)(cur.plane + j) * HoWo;
+      uint32_t* __restrict__ outp = a.y + (int64_t)(plane0 + j) * HoWo;
 
       // ---- A. interior rows: shifted copy shared -> global
       row_copy<NJ, FULL>(band + lane, outp + (ya + g.pt) * Wo + g.pl + lane, yb - ya, W, Wo, lane);
@@ -272,7 +261,7 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
       // ---- B. push: halo elements of other faces' planes (same cube, same channel) whose source
       //         pixel lies in rows [ya, yb) of this plane
       int ia[4], wd[4], cnt[4];
-      const uint4 pr4 = ptab[f * a.nb + (a.nb > 1 ? cur.band : 0)];
+      const uint4 pr4 = ptab[f * a.nb + band_i];
       const uint32_t prs[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -322,12 +311,9 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
       }
       if (np > 1 && ++c == a.C) { c = 0; ++nf; if (++f == 6) f = 0; }
     }
-    __syncwarp();                                  // every lane is done reading slot s:
-    if (pf.nt) {                                   // re-arm it with the tile `slots` steps ahead
-      if (lane == 0) issue(pf, s);
-      cursor_next(pf, a, u_stride);
-    }
-    cursor_next(cur, a, u_stride);
+    __syncwarp();                                  // every lane is done reading slot s and its meta:
+    if (lane == 0) arm(s);                         // re-arm it with the warp's next tile
+    __syncwarp();
     if (++s == slots) { s = 0; phase ^= 1u; }
   }
 #ifdef CP360_TRACE

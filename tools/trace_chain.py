@@ -93,13 +93,14 @@ def main():
                "fill_us": float(np.median((t2 - t1)[ok2])) / 1e3 if ok2.any() else None,
                "body_us": (end - int(t1.min())) / 1e3,
                "tail_spread_us": (end - int(np.percentile(t3, 10))) / 1e3,
-               "total_us": (end - start) / 1e3, "sms": int(len(set(smid[idx].tolist())))}
+               "total_us": (end - start) / 1e3, "sms": int(len(set(smid[idx].tolist()))),
+               "cta_end_pcts_us": [round((float(np.percentile(t3, q)) - int(t1.min())) / 1e3, 1) for q in (0, 10, 50, 90, 100)]}
         rows.append(row)
         prev_end = end
         print("%-3d %-10s %6d %9.1f %8s %8.1f %8.1f %8s %8.1f %8.1f %6d" % (
             li, row["kernel"], row["ctas"], row["start_us"], "-" if row["gap_us"] is None else "%.1f" % row["gap_us"],
             row["entry_spread_us"], row["prologue_us"], "-" if row["fill_us"] is None else "%.1f" % row["fill_us"],
-            row["body_us"], row["tail_spread_us"], row["sms"]))
+            row["body_us"], row["tail_spread_us"], row["sms"]), row["cta_end_pcts_us"])
     tot = (max(int(t[i, 3]) for i in order) - t_base) / 1e3
     print("records %d, launches %d, step span %.1f us; sum gaps %.1f us, sum tail spread %.1f us" % (
         n, len(launches), tot, sum(r["gap_us"] or 0 for r in rows), sum(r["tail_spread_us"] for r in rows)))
