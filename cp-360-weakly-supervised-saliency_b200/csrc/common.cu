@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,6 +37,56 @@ bool pdl_enabled() {
     return !(v && *v == '0');
   }();
   return on;
+}
+
+namespace {
+constexpr int kMaxDevices = 64;
+constexpr uint32_t kEagerPairs = 8192, kCapturePairs = 57344;
+struct CounterPool {
+  uint32_t* base = nullptr;
+  std::atomic<uint32_t> eager_seq{0}, capture_next{0};
+};
+CounterPool g_pools[kMaxDevices];
+std::mutex g_pool_mutex;
+}  // namespace
+
+uint32_t* acquire_work_counter(cudaStream_t st) {
+  static const bool enabled = [] {
+    const char* v = getenv("CP360_DYNAMIC");
+    return !(v && *v == '0');
+  }();
+  int dev = 0;
+  if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
+  CounterPool& pool = g_pools[dev];
+  if (!pool.base) {
+    if (capturing) return nullptr;                     // no allocation inside a capture
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!pool.base) {
+      uint32_t* p = nullptr;
+      const size_t bytes = (size_t)(kEagerPairs + kCapturePairs) * 2 * sizeof(uint32_t);
+      if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (p) cudaFree(p);
+        return nullptr;
+      }
+      pool.base = p;
+    }
+  }
+  uint32_t idx;
+  if (capturing) {
+    const uint32_t k = pool.capture_next.fetch_add(1, std::memory_order_relaxed);
+    if (k >= kCapturePairs) return nullptr;
+    idx = kEagerPairs + k;
+  } else {
+    idx = pool.eager_seq.fetch_add(1, std::memory_order_relaxed) % kEagerPairs;
+  }
+  return pool.base + 2 * (size_t)idx;
 }
 
 int sm_count() {

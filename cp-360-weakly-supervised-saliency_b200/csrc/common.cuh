@@ -48,6 +48,14 @@ int require_device();
 int sm_count();   // cached multiProcessorCount of the current device (148 on B200)
 bool pdl_enabled();   // CP360_PDL != 0 (default on)
 
+// Work counters for kernels that deal their tiles dynamically: a pair of zeroed device words
+// {next unit, finished CTAs} per launch; the last CTA of a launch zeroes its pair again. Eager
+// launches cycle through a ring (far longer than any launch queue), launches recorded by a stream
+// capture get pairs of their own that are never handed out again (a graph may be replayed at any
+// time). Returns nullptr when no pair can be provided (pool not yet created and the stream is
+// capturing, or capture pairs exhausted): the caller then falls back to its static partition.
+uint32_t* acquire_work_counter(cudaStream_t st);
+
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
 // attribute may become resident while its predecessor on the stream is still draining. Every
 // forward kernel calls pdl_trigger() first (lets ITS successor be scheduled early) and

@@ -436,11 +436,12 @@ static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* 
   if (kmax < kq) kmax = kq;
   if ((int64_t)6 * kmax * HW > 65535) return false;            // 16-bit staged source offsets
   const int stages = std::min(kCubeMaxStages, std::max(2, env_int("CP360_CUBE_STAGES", 3)));
-  a->C = C; a->kq = kq; a->kmax = kmax; a->qpc = C / kq; a->stages = stages;
-  a->n_quanta = (n_faces / 6) * a->qpc;
+  a->C = C; a->kmax = kmax; a->cblocks = (C + kmax - 1) / kmax; a->stages = stages;
+  a->n_chunks = (n_faces / 6) * a->cblocks;
+  a->work = nullptr;
   a->stage_words = 6 * kmax * HW;
-  a->lut_off = 128;
-  a->ring_off = (128 + 6 * HoWo * 4 + 127) & ~127;
+  a->lut_off = 3 * kCubeMaxStages * 8;
+  a->ring_off = (a->lut_off + 6 * HoWo * 4 + 127) & ~127;
   const size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
   if (smem > 220 * 1024) return false;
   *smem_out = smem;
@@ -458,9 +459,9 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_cube2_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cons_warps = std::min(31, std::max(1, env_int("CP360_CUBE_WARPS", 16)));
+  a.work = acquire_work_counter(st);
   // every CTA should own at least ~2 chunks
-  const int64_t chunks = (a.n_quanta * a.kq + a.kmax - 1) / a.kmax;
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((chunks + 1) / 2, (int64_t)sm_count() * per_sm));
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count() * per_sm));
   launch_kernel(cubepad_cube2_kernel, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;
@@ -541,9 +542,15 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
     a->n_units = (int32_t)((n_planes + a->k - 1) / a->k);
   }
   a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 3)));
-  a->order = env_int("CP360_ROW_ORDER", 2) == 2 ? 2 : 0;
+  // Measured on B200 (profiles/README.md): a fixed warp <-> window-position mapping beats handing tiles
+  // out grid-wide (orders 3, 4) at every site; many short bands per plane favour the skewed static
+  // round-robin, few long bands the CTA-local dynamic dealing.
+  a->order = env_int("CP360_ROW_ORDER", a->nb >= 8 ? 0 : 2);
+  if (a->order != 0 && a->order != 2 && a->order != 3) a->order = 4;
+  a->draw = std::min(16, std::max(1, env_int("CP360_ROW_DRAW", 2)));
+  a->work = nullptr;
   // the dynamic order hands out k = 0, 1, 2, ... per CTA and maps it to (k / 8) * warps_in_grid + ...
-  if ((int64_t)a->n_units + (int64_t)sm_count() * kRowWarps * 16 > 0x7fffffff) return false;
+  if ((int64_t)a->n_units + (int64_t)sm_count() * kRowWarps * 64 * 16 > 0x7fffffff) return false;
   a->d_upp = make_fastdiv((uint32_t)a->upp);
   a->d_C = make_fastdiv((uint32_t)C);
   return true;
@@ -555,6 +562,10 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   CP360_CHECK_ARG(row_plan(g, n_planes, C, &a), CP360_ERR_SHAPE,
                   "row kernel does not apply (H=%d, planes=%lld)", g.H, (long long)n_planes);
   a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
+  if (a.order >= 3) {
+    a.work = acquire_work_counter(st);
+    if (!a.work) a.order = 2;                                  // no counter pair available: CTA-local dealing
+  }
   const int align = std::max(16, env_int("CP360_ROW_SMEM_ALIGN", 128));
   a.ring_off = (int)((kRowBarBytes + 6 * a.nb * 16 + align - 1) / align * align) + env_int("CP360_ROW_SMEM_PAD", 0);
   const int slot_align = std::max(32, env_int("CP360_ROW_SLOT_ALIGN_WORDS", 32));

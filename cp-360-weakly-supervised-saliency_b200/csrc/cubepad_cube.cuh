@@ -13,9 +13,10 @@
 // LDS -> STG, consecutive lanes writing consecutive words of the padded plane (coalesced 128 B
 // streaming stores; the padded output never passes through shared memory).
 //
-// Work partition: the (cube, channel-quantum) index space is cut into one contiguous, balanced
-// range per CTA (no round-robin tail), walked in chunks of at most kmax channels that do not
-// cross a cube boundary.
+// Work partition: the chunk list (cube, channel block of kmax channels) is dealt dynamically — the
+// producer draws the next chunk id from a per-launch device counter (common.cuh:
+// acquire_work_counter) — so SMs that stream faster take more chunks; without a counter the chunks
+// are dealt round-robin. The chunk id staged in each ring slot travels with it in shared memory.
 #pragma once
 #include "common.cuh"
 #include "cubepad_geom.h"
@@ -28,38 +29,23 @@ constexpr int kCubeMaxStages = 8;
 struct Cube2Args {
   const uint32_t* x;
   uint32_t* y;
-  int64_t n_quanta;     // N * (C / kq)
+  uint32_t* work;       // {next chunk, finished CTAs} (zero at launch) or nullptr: chunks dealt round-robin
+  int64_t n_chunks;     // N * cblocks
   int32_t C;
-  int32_t kq;           // channel quantum (bulk-copy alignment)
-  int32_t kmax;         // channels per chunk (multiple of kq)
-  int32_t qpc;          // quanta per cube = C / kq
+  int32_t kmax;         // channels per chunk (multiple of the bulk-copy channel quantum)
+  int32_t cblocks;      // chunks per cube = ceil(C / kmax)
   int32_t stages;
   int32_t stage_words;  // 6 * kmax * H * W
   int32_t lut_off;      // byte offset of the position table in dynamic shared memory
   int32_t ring_off;     // byte offset of the input ring
 };
 
-struct CubeChunk {
-  int64_t q, q_end;     // next quantum / end of this CTA's range
-  int64_t n;            // cube index of the current chunk
-  int32_t c0, kl;       // first channel / number of channels (0: range exhausted)
-};
-
-__device__ __forceinline__ void chunk_next(CubeChunk& ck, const Cube2Args& a) {
-  if (ck.q >= ck.q_end) { ck.kl = 0; return; }
-  ck.n = ck.q / a.qpc;
-  const int cq = (int)(ck.q - ck.n * a.qpc);
-  const int take = (int)min((int64_t)min(a.kmax / a.kq, a.qpc - cq), ck.q_end - ck.q);
-  ck.c0 = cq * a.kq;
-  ck.kl = take * a.kq;
-  ck.q += take;
-}
-
 __global__ void __launch_bounds__(1024)
 cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [stages]
   uint64_t* empty = full + kCubeMaxStages;                                // [stages]
+  int64_t* chunk_of = reinterpret_cast<int64_t*>(empty + kCubeMaxStages); // [stages] chunk id staged there, -1: end
   uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + a.lut_off);      // [6*Ho*Wo]
   const uint32_t* ring = reinterpret_cast<const uint32_t*>(smem_raw + a.ring_off);
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo, n_pos = 6 * HoWo;
@@ -89,28 +75,41 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   pdl_wait();
   CP360_TRACE_T0(1);
 
-  CubeChunk ck;
-  ck.q = (a.n_quanta * blockIdx.x) / gridDim.x;
-  ck.q_end = (a.n_quanta * (blockIdx.x + 1)) / gridDim.x;
-  ck.kl = 0; ck.n = 0; ck.c0 = 0;
-  chunk_next(ck, a);
-
   if (warp == 0) {
-    // ---------------- producer
+    // ---------------- producer: draw chunks, stage them `stages` deep
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int it = 0; ck.kl; ++it) {
+      uint32_t ticket = a.work ? atomicAdd(a.work, 1u) : 0u;   // drawn one step ahead of its use
+      for (int64_t it = 0;; ++it) {
         if (it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
-        const uint32_t bytes = (uint32_t)(ck.kl * HW) * 4u;
+        int64_t q = (int64_t)blockIdx.x + it * gridDim.x;
+        if (a.work) {
+          q = (int64_t)ticket;
+          if (q < a.n_chunks) ticket = atomicAdd(a.work, 1u);
+        }
+        if (q >= a.n_chunks) {
+          chunk_of[s] = -1;
+          tma::mbar_arrive(&full[s]);                  // completes the phase: consumers see the end mark
+          break;
+        }
+        chunk_of[s] = q;
+        const int64_t n = q / a.cblocks;
+        const int c0 = (int)(q - n * a.cblocks) * a.kmax;
+        const int kl = min(a.kmax, a.C - c0);
+        const uint32_t bytes = (uint32_t)(kl * HW) * 4u;
         tma::mbar_expect_tx(&full[s], 6u * bytes);
         uint32_t* dst = const_cast<uint32_t*>(ring) + (size_t)s * a.stage_words;
-        const uint32_t* src = a.x + ((ck.n * 6) * a.C + ck.c0) * HW;
+        const uint32_t* src = a.x + ((n * 6) * a.C + c0) * HW;
 #pragma unroll
         for (int f = 0; f < 6; ++f)
           tma::bulk_load(dst + f * fstride, src + (int64_t)f * a.C * HW, bytes, &full[s]);
-        chunk_next(ck, a);
         if (++s == a.stages) { s = 0; ph ^= 1u; }
+      }
+      if (a.work && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {   // last CTA: hand the pair back zeroed
+        a.work[0] = 0;
+        a.work[1] = 0;
+        __threadfence();
       }
     }
     return;
@@ -121,14 +120,18 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   const int64_t CHoWo = (int64_t)a.C * HoWo;
   int s = 0;
   uint32_t ph = 0;
-  while (ck.kl) {
-    const uint32_t* in_s = ring + (size_t)s * a.stage_words;
-    uint32_t* __restrict__ out = a.y + ((ck.n * 6) * a.C + ck.c0) * HoWo;
-    const int kl = ck.kl;
+  while (true) {
     tma::mbar_wait(&full[s], ph);
+    const int64_t q = chunk_of[s];
+    if (q < 0) break;
 #ifdef CP360_TRACE
     if (lane == 0) CP360_TRACE_MIN(2);
 #endif
+    const int64_t n = q / a.cblocks;
+    const int c0 = (int)(q - n * a.cblocks) * a.kmax;
+    const int kl = min(a.kmax, a.C - c0);
+    const uint32_t* in_s = ring + (size_t)s * a.stage_words;
+    uint32_t* __restrict__ out = a.y + ((n * 6) * a.C + c0) * HoWo;
 #pragma unroll 1
     for (int e = ctid; e < n_pos; e += n_cons) {
       const uint32_t l = lut[e];
@@ -148,7 +151,6 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
     }
     __syncwarp();
     if (lane == 0) tma::mbar_arrive(&empty[s]);
-    chunk_next(ck, a);
     if (++s == a.stages) { s = 0; ph ^= 1u; }
   }
 #ifdef CP360_TRACE

@@ -37,7 +37,8 @@ constexpr int kRowThreads = kRowWarps * 32;
 constexpr int kRowMaxSlots = 8;
 constexpr int kRowMetaOff = kRowWarps * kRowMaxSlots * 8;            // per-slot (plane, band) of the tile in flight
 constexpr int kRowCtrOff = 2 * kRowMetaOff;                            // CTA-wide unit counter
-constexpr int kRowBarBytes = kRowCtrOff + 16;
+constexpr int kRowGrpOff = kRowCtrOff + 16;                          // order 4: ring of 8 {group base, tag}
+constexpr int kRowBarBytes = kRowGrpOff + 64;
 
 // n / d for 0 <= n < 2^31 as umulhi(n, m) >> s  (m == 0: d == 1)
 struct FastDiv { uint32_t m, s; };
@@ -71,7 +72,12 @@ struct RowArgs {
   int32_t slots;
   int32_t ring_off;         // byte offset of the rings inside dynamic shared memory
   int32_t order;            // 0: units dealt round-robin to the grid's warps (static); 2: dealt round-robin to
-                            //    CTAs in groups of 8, warps of a CTA draw from the CTA's list (dynamic)
+                            //    CTAs in groups of 8, warps of a CTA draw from the CTA's list; 3: every warp
+                            //    draws `draw` consecutive units at a time from one grid-wide counter; 4: CTAs
+                            //    draw groups of 8 consecutive units from the grid-wide counter, their warps draw
+                            //    from the CTA's current group
+  int32_t draw;
+  uint32_t* work;           // order 3: {next unit, finished CTAs}, zero at launch, zeroed again by the last CTA
   FastDiv d_upp, d_C;
 };
 
@@ -169,6 +175,8 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   const int gw = blockIdx.x * kRowWarps + warp, GW = gridDim.x * kRowWarps;
   int2* meta = reinterpret_cast<int2*>(smem_raw + kRowMetaOff) + warp * kRowMaxSlots;
   int* ctr = reinterpret_cast<int*>(smem_raw + kRowCtrOff);
+  volatile int* gbase = reinterpret_cast<volatile int*>(smem_raw + kRowGrpOff);   // [8]
+  volatile int* gtag = gbase + 8;                                                 // [8] group number held, -1: none
 
   // lane 0: bulk-load the tile (plane, band) into slot s
   auto issue = [&](int plane, int band, int s) {
@@ -188,10 +196,27 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     tma::bulk_load(ring + s * a.slot_words, a.x + w0, bytes, &bar[s]);
   };
   // lane 0: take the warp's next unit, publish it as slot s's tile and start its load
-  int my_k = 0;
-  auto arm = [&](int s) {
+  int my_k = 0, u_next = 0, u_left = 0;
+  uint32_t ticket = 0;                                 // order 3: drawn one step ahead, so that the
+  auto arm = [&](int s) {                              // atomic's round trip never sits on the re-arm path
     int u;
-    if (a.order == 2) {
+    if (a.order == 3) {
+      if (u_left == 0) {
+        // clamp: the counter keeps growing by `draw` per probe of an exhausted warp
+        u_next = (int)min(ticket, (uint32_t)a.n_units);
+        u_left = a.draw;
+        ticket = atomicAdd(a.work, (uint32_t)a.draw);
+      }
+      u = u_next++;
+      --u_left;
+    } else if (a.order == 4) {
+      const int k = atomicAdd(ctr, 1);
+      const int gl = k >> 3;
+      while (gtag[gl & 7] != gl) {}                    // published two groups ahead; practically never spins
+      u = gbase[gl & 7] + (k & 7);
+      if ((k & 7) == 0) ticket = 1;                    // this warp fetches group gl + 2 once its own load is on its way
+      u_next = gl + 2;
+    } else if (a.order == 2) {
       const int k = atomicAdd(ctr, 1);
       u = (k >> 3) * GW + blockIdx.x * kRowWarps + (k & 7);
     } else {
@@ -205,6 +230,13 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     } else {
       meta[s] = make_int2(-1, 0);
     }
+    if (a.order == 4 && ticket) {
+      ticket = 0;
+      const int gb = (int)min(atomicAdd(a.work, 8u), (uint32_t)a.n_units);
+      gbase[u_next & 7] = gb;
+      __threadfence_block();
+      gtag[u_next & 7] = u_next;
+    }
   };
 
   CP360_TRACE_BEGIN(1)
@@ -217,13 +249,24 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     const int ya = a.nb > 1 ? b * a.Rb : 0, yb = a.nb > 1 ? min(ya + a.Rb, H) : H;
     reinterpret_cast<uint32_t*>(ptab)[i] = push_range(g.push[ff][e], ya, yb);
   }
-  __syncthreads();                                     // the only block-wide sync of the kernel
+  if (threadIdx.x < 8) gtag[threadIdx.x] = -1;
+  __syncthreads();                                     // the only block-wide sync before the end of the kernel
   pdl_wait();
   CP360_TRACE_T0(1);
+  if (a.order == 4 && threadIdx.x == 0) {              // groups 0 and 1 of this CTA
+    const uint32_t g0 = atomicAdd(a.work, 8u), g1 = atomicAdd(a.work, 8u);
+    gbase[0] = (int)min(g0, (uint32_t)a.n_units);
+    gbase[1] = (int)min(g1, (uint32_t)a.n_units);
+    __threadfence_block();
+    gtag[0] = 0;
+    gtag[1] = 1;
+  }
 
   if (lane == 0) {
     for (int s = 0; s < slots; ++s) tma::mbar_init(&bar[s], 1);
     tma::fence_mbar_init();
+    if (a.order == 3) ticket = atomicAdd(a.work, (uint32_t)a.draw);
+    if (a.order == 4) ticket = 0;
     for (int s = 0; s < slots; ++s) arm(s);
   }
   __syncwarp();
@@ -319,6 +362,16 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
 #ifdef CP360_TRACE
   if (lane == 0) CP360_TRACE_MAX(3);
 #endif
+  if (a.order >= 3) {
+    __syncthreads();                                   // every warp of the CTA has drawn its last unit
+    if (threadIdx.x == 0) {
+      if (atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {   // last CTA of the launch: hand the pair back zeroed
+        a.work[0] = 0;
+        a.work[1] = 0;
+        __threadfence();
+      }
+    }
+  }
 }
 
 }  // namespace cp360
