@@ -355,6 +355,14 @@ def run_b200(args, rank, world, local_rank):
         except Exception:
             pass
 
+    # tilings the first-call autotuner settled on (per distinct CubePad site)
+    import ctypes
+    tuning = {}
+    for (C, H, pp) in dict.fromkeys(pipe.sites):
+        buf = ctypes.create_string_buffer(160)
+        lib.cp360_cubepad_tune_info(6 * B, C, H, H, pp, pp, pp, pp, buf, 160)
+        tuning["%dx%dx%d p%d" % (C, H, H, pp)] = buf.value.decode() or "heuristic"
+
     # ---- end to end: pinned host frames in, host saliency maps out, copies inside the region.
     # Headline = uint8 frames (what a video decoder hands over; converted on the GPU exactly as the
     # reference's float32(u8/255.0)); the float32-host-frame variant is reported beside it.
@@ -412,7 +420,7 @@ def run_b200(args, rank, world, local_rank):
                                  % (pipe.bytes_per_frame() * B / 1e9),
                            "algorithmic_bytes_per_frame": pipe.bytes_per_frame()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+                "roofline": roofline, "kernels": kernels, "tuning": tuning, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

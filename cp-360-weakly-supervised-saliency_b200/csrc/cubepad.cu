@@ -19,6 +19,10 @@
 // The geometry is the 4x6 affine plate table of cubepad_geom.h, identical for all kernels and
 // for the host-side index map exported to the parity tests.
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -412,6 +416,23 @@ static int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
+// One tiling choice for a CubePad problem. 0 = "not set": the plan functions fall back to their
+// heuristics. Filled by the first-call autotuner (below) and consulted through knob(); an
+// environment variable of the same knob always wins (experiments, tools/).
+struct TuneCfg {
+  int algo = 0;
+  int row_rb = 0, row_order1 = 0 /* order + 1 */, row_slots = 0, row_tile_kb = 0;
+  int cube_stage_kb = 0, cube_stages = 0, cube_warps = 0;
+  float us = 0.f;
+};
+static thread_local const TuneCfg* t_tune = nullptr;
+
+static int knob(const char* env_name, int tuned, int dflt) {
+  const char* v = getenv(env_name);
+  if (v && *v) return atoi(v);
+  return tuned > 0 ? tuned : dflt;
+}
+
 // Persistent kernels partition their work statically over one CTA per SM. Under programmatic
 // dependent launch a successor's CTAs become resident wherever room appears first, so two of them
 // could share an SM while another SM gets none; asking for more than half of the SM's shared
@@ -429,13 +450,13 @@ static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* 
   int kq = 1;
   while (kq <= 4 && (kq * HW) % 4) kq <<= 1;                   // 16 B granularity of the bulk copies
   if (kq > 4 || C % kq) return false;
-  const int stage_kb = std::max(1, env_int("CP360_CUBE_STAGE_KB", 48));
+  const int stage_kb = std::max(1, knob("CP360_CUBE_STAGE_KB", t_tune ? t_tune->cube_stage_kb : 0, 48));
   int kmax = (stage_kb * 1024) / (6 * HW * 4);
   kmax = std::min(kmax, C);
   kmax -= kmax % kq;
   if (kmax < kq) kmax = kq;
   if ((int64_t)6 * kmax * HW > 65535) return false;            // 16-bit staged source offsets
-  const int stages = std::min(kCubeMaxStages, std::max(2, env_int("CP360_CUBE_STAGES", 3)));
+  const int stages = std::min(kCubeMaxStages, std::max(2, knob("CP360_CUBE_STAGES", t_tune ? t_tune->cube_stages : 0, 3)));
   a->C = C; a->kmax = kmax; a->cblocks = (C + kmax - 1) / kmax; a->stages = stages;
   a->n_chunks = (n_faces / 6) * a->cblocks;
   a->work = nullptr;
@@ -458,7 +479,7 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   smem = exclusive_smem(smem, per_sm);
   CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_cube2_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int cons_warps = std::min(31, std::max(1, env_int("CP360_CUBE_WARPS", 16)));
+  const int cons_warps = std::min(31, std::max(1, knob("CP360_CUBE_WARPS", t_tune ? t_tune->cube_warps : 0, 16)));
   a.work = acquire_work_counter(st);
   // every CTA should own at least ~2 chunks
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count() * per_sm));
@@ -502,12 +523,12 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
   const int HW = g.H * g.W;
   if (n_planes <= 0 || n_planes > 0x3fffffff) return false;
   if ((n_planes * HW) % 4) return false;                       // input ends on a 16 B boundary
-  const int target_words = std::max(1, env_int("CP360_ROW_TILE_KB", 4)) * 256;
+  const int target_words = std::max(1, knob("CP360_ROW_TILE_KB", t_tune ? t_tune->row_tile_kb : 0, 4)) * 256;
   a->C = C;
   a->n_planes = (int32_t)n_planes;
   a->total_in_words = n_planes * HW;
   const int rb_w = env_int("CP360_ROW_RB_W", 0);               // tuning knob: CP360_ROW_RB applies to this W only
-  const int rb_env = (rb_w == 0 || rb_w == g.W) ? env_int("CP360_ROW_RB", 0) : 0;
+  const int rb_env = (rb_w == 0 || rb_w == g.W) ? knob("CP360_ROW_RB", t_tune ? t_tune->row_rb : 0, 0) : 0;
   if ((rb_env > 0 && rb_env < g.H) || (rb_env == 0 && HW > target_words + target_words / 2)) {   // bands of rows inside one plane
     // ~4.5 KB tiles (5 KB for narrow rows) measured best on B200; see profiles/README.md
     int rb = std::max(1, (target_words + target_words / 8) / g.W);
@@ -541,11 +562,13 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
     a->slot_words = ((a->k * HW + 8) + 31) & ~31;
     a->n_units = (int32_t)((n_planes + a->k - 1) / a->k);
   }
-  a->slots = std::min(kRowMaxSlots, std::max(2, env_int("CP360_ROW_SLOTS", 3)));
+  a->slots = std::min(kRowMaxSlots, std::max(2, knob("CP360_ROW_SLOTS", t_tune ? t_tune->row_slots : 0, 3)));
   // Measured on B200 (profiles/README.md): a fixed warp <-> window-position mapping beats handing tiles
   // out grid-wide (orders 3, 4) at every site; many short bands per plane favour the skewed static
   // round-robin, few long bands the CTA-local dynamic dealing.
-  a->order = env_int("CP360_ROW_ORDER", a->nb >= 8 ? 0 : 2);
+  const char* order_env = getenv("CP360_ROW_ORDER");
+  a->order = (order_env && *order_env) ? atoi(order_env)
+             : (t_tune && t_tune->row_order1 > 0) ? t_tune->row_order1 - 1 : (a->nb >= 8 ? 0 : 2);
   if (a->order != 0 && a->order != 2 && a->order != 3) a->order = 4;
   a->draw = std::min(16, std::max(1, env_int("CP360_ROW_DRAW", 2)));
   a->work = nullptr;
@@ -620,6 +643,155 @@ static int pick_algo(const CubePadGeom& g, int64_t n_faces, int C, bool fast_ok)
   return ALGO_GENERIC;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// first-call autotuner
+// ------------------------------------------------------------------------------------------
+// Which tiling streams fastest depends on the shape in ways no static rule captured (band height
+// and dealing order move a site between ~3.4 and ~4.8 TB/s, profiles/README.md), so the first AUTO
+// call for a problem (device, geometry, C, batch) times a handful of candidate tilings on the
+// caller's own tensors — CubePad is idempotent, every candidate writes the same y — with a cache
+// flush in between, and remembers the winner. Not done while the stream is being captured, for
+// small problems, or with CP360_AUTOTUNE=0; then the heuristics of the plan functions apply.
+struct TuneKey {
+  int dev, H, pl, pr, pt, pd, C;
+  int64_t n_faces;
+  bool operator<(const TuneKey& o) const {
+    return std::tie(dev, H, pl, pr, pt, pd, C, n_faces) < std::tie(o.dev, o.H, o.pl, o.pr, o.pt, o.pd, o.C, o.n_faces);
+  }
+};
+static std::map<TuneKey, TuneCfg> g_tuned;
+static std::mutex g_tuned_mutex;
+
+static TuneKey tune_key(const CubePadGeom& g, int64_t n_faces, int C) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return TuneKey{dev, g.H, g.pl, g.pr, g.pt, g.pd, C, n_faces};
+}
+
+static bool tuned_lookup(const TuneKey& k, TuneCfg* out) {
+  std::lock_guard<std::mutex> lock(g_tuned_mutex);
+  auto it = g_tuned.find(k);
+  if (it == g_tuned.end()) return false;
+  *out = it->second;
+  return true;
+}
+
+static int run_cfg(const TuneCfg& cfg, const void* x, void* y, int64_t n_faces, int C, const CubePadGeom& g,
+                   cudaStream_t st) {
+  t_tune = &cfg;
+  const int rc = cfg.algo == ALGO_CUBE2 ? launch_cube2(x, y, n_faces, C, g, st)
+                                         : launch_row(x, y, n_faces * C, C, g, st);
+  t_tune = nullptr;
+  return rc;
+}
+
+static std::vector<TuneCfg> tune_candidates(const CubePadGeom& g, int64_t n_faces, int C) {
+  std::vector<TuneCfg> out;
+  const int HW = g.H * g.W;
+  RowArgs ra; Cube2Args ca; size_t smem; int per_sm;
+  if (g.H >= 24 && row_plan(g, n_faces * C, C, &ra)) {
+    if (HW * 4 > 6144) {                                        // bands of rows: band height x dealing order
+      std::vector<int> rbs;
+      for (int bytes : {3072, 3584, 4096, 4608, 5120, 6144}) {
+        const int rb = std::max(1, (bytes + g.W * 2) / (g.W * 4));
+        if (rb < g.H && std::find(rbs.begin(), rbs.end(), rb) == rbs.end()) rbs.push_back(rb);
+      }
+      for (int rb : rbs)
+        for (int order : {0, 2}) {
+          TuneCfg c; c.algo = ALGO_ROW; c.row_rb = rb; c.row_order1 = order + 1; c.row_slots = 3;
+          out.push_back(c);
+        }
+    } else {                                                    // whole planes per tile
+      for (int kb : {4, 8})
+        for (int order : {0, 2}) {
+          TuneCfg c; c.algo = ALGO_ROW; c.row_tile_kb = kb; c.row_order1 = order + 1; c.row_slots = 3;
+          out.push_back(c);
+        }
+    }
+  }
+  if (g.H <= 45)
+    for (int kb : {24, 48})
+      for (int stages : {3, 4})
+        for (int warps : {8, 16}) {
+          TuneCfg c; c.algo = ALGO_CUBE2; c.cube_stage_kb = kb; c.cube_stages = stages; c.cube_warps = warps;
+          t_tune = &c;
+          const bool ok = cube2_plan(g, n_faces, C, &ca, &smem, &per_sm);
+          t_tune = nullptr;
+          if (ok) out.push_back(c);
+        }
+  return out;
+}
+
+// Returns true and fills *best if tuning ran (y then holds the result of a complete launch).
+static bool autotune(const void* x, void* y, int64_t n_faces, int C, const CubePadGeom& g, cudaStream_t st,
+                     TuneCfg* best) {
+  std::vector<TuneCfg> cands = tune_candidates(g, n_faces, C);
+  if (cands.size() < 2) return false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  void* scratch = nullptr;
+  const size_t scratch_bytes = (size_t)160 << 20;               // > L2 (126 MB)
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess ||
+      cudaMalloc(&scratch, scratch_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return false;
+  }
+  auto time_cfg = [&](const TuneCfg& c, int reps) -> float {
+    float best_ms = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+      cudaMemsetAsync(scratch, 0, scratch_bytes, st);          // cold, dirty L2 as in a chain of kernels
+      cudaEventRecord(e0, st);
+      if (run_cfg(c, x, y, n_faces, C, g, st) != CP360_OK) return 1e30f;
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); return 1e30f; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best_ms = std::min(best_ms, ms);
+    }
+    return best_ms;
+  };
+  int bi = -1;
+  for (size_t i = 0; i < cands.size(); ++i) {
+    const float ms = time_cfg(cands[i], 3);
+    cands[i].us = ms * 1e3f;
+    if (ms < 1e29f && (bi < 0 || ms < cands[bi].us * 1e-3f)) bi = (int)i;
+  }
+  if (bi >= 0 && cands[bi].algo == ALGO_ROW) {                  // ring depth around the winner
+    for (int slots : {2, 4}) {
+      TuneCfg c = cands[bi];
+      c.row_slots = slots;
+      const float ms = time_cfg(c, 3);
+      c.us = ms * 1e3f;
+      if (ms < cands[bi].us * 1e-3f) { cands.push_back(c); bi = (int)cands.size() - 1; }
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  if (bi < 0) return false;
+  *best = cands[bi];
+  if (env_int("CP360_AUTOTUNE_VERBOSE", 0)) {
+    fprintf(stderr, "[cp360 autotune] H=%d C=%d faces=%lld p=%d%d%d%d:", g.H, C, (long long)n_faces, g.pl, g.pr, g.pt, g.pd);
+    for (const TuneCfg& c : cands)
+      fprintf(stderr, " %s(rb%d o%d s%d kb%d|kb%d st%d w%d)=%.1f", c.algo == ALGO_ROW ? "row" : "cube", c.row_rb,
+              c.row_order1 - 1, c.row_slots, c.row_tile_kb, c.cube_stage_kb, c.cube_stages, c.cube_warps, c.us);
+    fprintf(stderr, "\n");
+  }
+  // leave y written by the winner's kernel (any candidate writes the same values)
+  return run_cfg(*best, x, y, n_faces, C, g, st) == CP360_OK;
+}
+
+static bool autotune_allowed(int64_t n_faces, int C, const CubePadGeom& g, cudaStream_t st) {
+  if (!env_int("CP360_AUTOTUNE", 1)) return false;
+  const int64_t bytes = n_faces * C * ((int64_t)g.H * g.W + (int64_t)g.Ho * g.Wo) * 4;
+  if (bytes < (int64_t)env_int("CP360_AUTOTUNE_MIN_MB", 16) << 20) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs == cudaStreamCaptureStatusNone;
+}
+
 }  // namespace cp360
 
 using namespace cp360;
@@ -657,7 +829,26 @@ int cp360_cubepad_pick_algo(int64_t n_faces, int64_t C, int H, int W, int pl, in
     set_error("CubePad needs square faces and 0 <= pad <= H");
     return -CP360_ERR_SHAPE;
   }
+  TuneCfg cfg;
+  if (elem_bytes == 4 && aligned16 != 0 && tuned_lookup(tune_key(g, n_faces, (int)C), &cfg)) return cfg.algo;
   return pick_algo(g, n_faces, (int)C, elem_bytes == 4 && aligned16 != 0);
+}
+
+int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,
+                            char* buf, int buf_len) {
+  CubePadGeom g;
+  CP360_CHECK_ARG(buf && buf_len > 0, CP360_ERR_BAD_ARG, "null buffer");
+  buf[0] = 0;
+  if (!make_geom(H, W, pl, pr, pt, pd, &g) || C < 0 || C > 0x7fffffff) return CP360_OK;
+  TuneCfg c;
+  if (!tuned_lookup(tune_key(g, n_faces, (int)C), &c)) return CP360_OK;
+  if (c.algo == ALGO_ROW)
+    snprintf(buf, (size_t)buf_len, "row rb=%d tile_kb=%d order=%d slots=%d (%.1f us)", c.row_rb, c.row_tile_kb,
+             c.row_order1 - 1, c.row_slots, c.us);
+  else
+    snprintf(buf, (size_t)buf_len, "cube stage_kb=%d stages=%d warps=%d (%.1f us)", c.cube_stage_kb, c.cube_stages,
+             c.cube_warps, c.us);
+  return CP360_OK;
 }
 
 int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
@@ -677,6 +868,16 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
   const int64_t n_planes = n_faces * C;
   const bool fast_ok = elem_bytes == 4 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0;
 
+  if (algo == ALGO_AUTO && fast_ok) {
+    const TuneKey key = tune_key(g, n_faces, (int)C);
+    TuneCfg cfg;
+    if (tuned_lookup(key, &cfg)) return run_cfg(cfg, x, y, n_faces, (int)C, g, st);
+    if (autotune_allowed(n_faces, (int)C, g, st) && autotune(x, y, n_faces, (int)C, g, st, &cfg)) {
+      std::lock_guard<std::mutex> lock(g_tuned_mutex);
+      g_tuned[key] = cfg;
+      return CP360_OK;
+    }
+  }
   if (algo == ALGO_AUTO) algo = pick_algo(g, n_faces, (int)C, fast_ok);
   switch (algo) {
     case ALGO_CUBE:

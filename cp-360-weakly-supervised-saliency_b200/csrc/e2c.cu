@@ -68,24 +68,24 @@ e2c_kernel(const float* __restrict__ frames, const uint32_t* __restrict__ packed
   }
 }
 
-// C == 3, 16 B-aligned rows: the six floats of a tap pair (pixels x0, x0+1) are 24 contiguous bytes
-// at a 4 B-aligned address. Six scalar loads per row make the L1 serve the same ~25 sectors six
-// times per warp (ncu: 25 sectors/request, lg_throttle); instead each lane fetches the 16 B-aligned
-// window that holds them with two (three when it starts 12 B in) 128-bit loads and picks its
-// floats with selects. Same arithmetic as e2c_kernel, bit-identical results.
-__device__ __forceinline__ float pick4(const float (&w)[12], int k, int o) {
-  return o == 0 ? w[k] : o == 1 ? w[k + 1] : o == 2 ? w[k + 2] : w[k + 3];
-}
+// C == 3, 16 B-aligned rows and frames: the six floats of a tap pair (pixels x0, x0+1) are 24
+// contiguous bytes at a 4 B-aligned address. Six scalar loads per row make the L1 serve the same
+// ~25 sectors six times per warp (ncu: 25 sectors/request, lg_throttle); instead each lane fetches
+// the 16 B-aligned window that holds them with two (three when it starts 12 B in) 128-bit loads and
+// shifts its floats into place with a two-stage select (by 2 words, then by 1). A thread keeps
+// its pixel (map entry, weights, window offsets) for kE2cFramesPerThread frames. Same arithmetic
+// as e2c_kernel, bit-identical results.
+constexpr int kE2cFramesPerThread = 4;
 
-__device__ __forceinline__ void load_window(const float* p, const float* end, int o, float (&w)[12]) {
-  const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 a = __ldg(q);
-  const float4 b = reinterpret_cast<const float*>(q + 2) <= end ? __ldg(q + 1) : z;
-  const float4 c = (o == 3 && reinterpret_cast<const float*>(q + 3) <= end) ? __ldg(q + 2) : z;
-  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-  w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+// v[0..5] = w[o..o+5]; hi = w[8] (needed for o == 3 only)
+__device__ __forceinline__ void realign6(const float4& a, const float4& b, float hi, int o, float (&v)[6]) {
+  const float w[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, hi};
+  const bool s2 = (o & 2) != 0, s1 = (o & 1) != 0;
+  float t[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) t[k] = s2 ? w[k + 2] : w[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = s1 ? t[k + 1] : t[k];
 }
 
 template <int LAYOUT, bool NORM>
@@ -109,30 +109,65 @@ e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ pa
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
   const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;   // BORDER_CONSTANT 0
-  const float* end = frames + B * (int64_t)Hin * Win * C;
+  // window of row y0 inside a frame, in floats; frames and rows are 16 B aligned, so the window
+  // alignment o is the same for both rows and every frame
+  const int frame_floats = Hin * Win * C, row_floats = Win * C;
+  const int e0 = (y0 * Win + x0) * C;
+  const int o = e0 & 3;
+  const int a0 = e0 - o;                                   // aligned start of the row-y0 window
+  const int need = o == 3 ? 12 : 8;                        // floats fetched per window
+  // only the last frame can run off the end of the buffer (elsewhere the overrun lands in the next frame)
+  const bool risky = (y1_ok ? a0 + row_floats : a0) + need > frame_floats;
+  const int pix = oy * w + ox;
 
-  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
-    const float* row0 = frames + ((b * Hin + y0) * (int64_t)Win + x0) * C;
-    const int o = (int)((reinterpret_cast<uintptr_t>(row0) >> 2) & 3);   // same for row1: pitch % 16 == 0
-    float r0[12], r1[12];
-    load_window(row0, end, o, r0);
-    if (y1_ok) load_window(row0 + (int64_t)Win * C, end, o, r1);
+  for (int64_t b_begin = (int64_t)blockIdx.z * kE2cFramesPerThread; b_begin < B;
+       b_begin += (int64_t)gridDim.z * kE2cFramesPerThread) {
+  const int64_t b_end = min(B, b_begin + kE2cFramesPerThread);
+#pragma unroll 2
+  for (int64_t b = b_begin; b < b_end; ++b) {
+    const float* fr = frames + b * frame_floats;
+    const float4* q0 = reinterpret_cast<const float4*>(fr + a0);
+    const float4* q1 = reinterpret_cast<const float4*>(fr + a0 + row_floats);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r0a, r0b, r1a = z, r1b = z;
+    float r0c = 0.f, r1c = 0.f;
+    if (!(risky && b == B - 1)) {
+      r0a = __ldg(q0); r0b = __ldg(q0 + 1);
+      if (o == 3) r0c = __ldg(reinterpret_cast<const float*>(q0 + 2));
+      if (y1_ok) {
+        r1a = __ldg(q1); r1b = __ldg(q1 + 1);
+        if (o == 3) r1c = __ldg(reinterpret_cast<const float*>(q1 + 2));
+      }
+    } else {                                               // tail of the buffer: guarded element loads
+      float t0[9], t1[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        t0[k] = a0 + k < frame_floats ? __ldg(fr + a0 + k) : 0.f;
+        t1[k] = (y1_ok && a0 + row_floats + k < frame_floats) ? __ldg(fr + a0 + row_floats + k) : 0.f;
+      }
+      r0a = make_float4(t0[0], t0[1], t0[2], t0[3]); r0b = make_float4(t0[4], t0[5], t0[6], t0[7]); r0c = t0[8];
+      r1a = make_float4(t1[0], t1[1], t1[2], t1[3]); r1b = make_float4(t1[4], t1[5], t1[6], t1[7]); r1c = t1[8];
+    }
+    float v0[6], v1[6];
+    realign6(r0a, r0b, r0c, o, v0);
+    realign6(r1a, r1b, r1c, o, v1);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float s00 = pick4(r0, c, o);
-      const float a01 = x1_ok ? pick4(r0, C + c, o) : 0.0f;
-      const float a10 = y1_ok ? pick4(r1, c, o) : 0.0f;
-      const float a11 = (x1_ok && y1_ok) ? pick4(r1, C + c, o) : 0.0f;
+      const float s00 = v0[c];
+      const float a01 = x1_ok ? v0[C + c] : 0.0f;
+      const float a10 = y1_ok ? v1[c] : 0.0f;
+      const float a11 = (x1_ok && y1_ok) ? v1[C + c] : 0.0f;
       float v = __fmul_rn(s00, w00);
       v = __fadd_rn(v, __fmul_rn(a01, w01));
       v = __fadd_rn(v, __fmul_rn(a10, w10));
       v = __fadd_rn(v, __fmul_rn(a11, w11));
       if (NORM) v = __fdiv_rn(__fsub_rn(v, nrm.mean[c]), nrm.std[c]);   // utils/utils.py:28-33
       if (LAYOUT == CP360_LAYOUT_NCHW)
-        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox, v);
+        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + pix, v);
       else
-        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+        faces[((b * 6 + f) * (int64_t)ww + pix) * C + c] = v;
     }
+  }
   }
   CP360_TRACE_T0(3);
 }
@@ -339,8 +374,10 @@ extern "C" int cp360_e2c_fwd(const float* frames, const uint32_t* packed, float*
     else launch_c<CC, CP360_LAYOUT_NHWC>(norm, grid, block, st, frames, packed, faces, B, Hin,  \
                                           Win, w, nrm);                                         \
     break;
-  const bool vec_ok = C == 3 && ((uintptr_t)frames % 16) == 0 && ((int64_t)Win * C * 4) % 16 == 0;
+  const bool vec_ok = C == 3 && ((uintptr_t)frames % 16) == 0 && ((int64_t)Win * C * 4) % 16 == 0 &&
+                      ((int64_t)Hin * Win * C * 4) % 16 == 0;
   if (vec_ok) {
+    grid.z = (unsigned)std::min<int64_t>((B + kE2cFramesPerThread - 1) / kE2cFramesPerThread, 65535);
     if (nchw) {
       if (norm) launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NCHW, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
       else launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NCHW, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);

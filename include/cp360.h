@@ -88,9 +88,14 @@ CP360_API int cp360_cubepad_fwd_algo(const void* x_dev, void* y_dev, int64_t n_f
                            int pl, int pr, int pt, int pd, int elem_bytes, int algo, void* stream);
 
 /* Host: the kernel cp360_cubepad_fwd (algo 0) runs for this problem: 1 generic, 3 band, 4
- * cube-tile, 5 row; aligned16 = both tensor pointers are 16 B aligned. Negative: -status. */
+ * cube-tile (v1), 5 row, 6 cube-tile; aligned16 = both tensor pointers are 16 B aligned. Negative: -status. */
 CP360_API int cp360_cubepad_pick_algo(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt,
                             int pd, int elem_bytes, int aligned16);
+
+/* Host: human-readable tiling the first-call autotuner chose for this problem on the current device
+ * ("" if the problem has not been tuned: too small, stream was capturing, CP360_AUTOTUNE=0). */
+CP360_API int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,
+                            char* buf, int buf_len);
 
 /* Device, fp32: gx[6N,C,H,W] = dCubePad^T(gy[6N,C,Ho,Wo]) — every input pixel receives the sum
  * of the gradients of all output pixels that copied it (what autograd derives from the

@@ -8,6 +8,7 @@ against cv2.remap's fixed-point arithmetic (tolerance 0, stricter than the 1e-5 
 c2e maps max-abs <= 1e-5 (fp32).
 """
 import hashlib
+import ctypes
 import zlib
 
 import numpy as np
@@ -89,6 +90,26 @@ def test_cubepad_vs_oracle(dev, shape, pad, algo):
             raise
         pytest.skip("algo %d does not apply: %s" % (algo, e))
     np.testing.assert_array_equal(y.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape,pad", [((12, 16, 64, 64), 1), ((6, 24, 32, 32), 1), ((12, 64, 16, 16), 1),
+                                       ((6, 3, 128, 128), 3), ((6, 40, 28, 28), [1, 2, 2, 1])])
+def test_cubepad_autotuned_path(dev, shape, pad, monkeypatch):
+    """First AUTO call of a problem times candidate tilings on the caller's tensors and caches the
+    winner; the tuned launch (and every candidate it tried) must stay bit-exact."""
+    monkeypatch.setenv("CP360_AUTOTUNE_MIN_MB", "0")
+    x = np.random.default_rng(zlib.crc32(repr(shape).encode())).standard_normal(shape).astype(np.float32)
+    want = ocp.cubepad(x, pad)
+    xt = torch.from_numpy(x).to(dev)
+    pads = cp360_b200.get_pad_size(pad)
+    y1 = cp360_b200.cubepad_forward(xt, pads)           # tunes
+    buf = ctypes.create_string_buffer(256)
+    n, c, h, w_ = shape
+    _lib.check(_lib.lib().cp360_cubepad_tune_info(n, c, h, w_, pads[0], pads[1], pads[2], pads[3], buf, 256))
+    assert buf.value, "problem was not tuned"
+    y2 = cp360_b200.cubepad_forward(xt, pads)           # cached configuration
+    np.testing.assert_array_equal(y1.cpu().numpy(), want)
+    np.testing.assert_array_equal(y2.cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("dtype", [torch.uint8, torch.float16, torch.bfloat16, torch.float64, torch.int64,
@@ -222,6 +243,20 @@ def test_e2c_vs_oracle_channels_and_batch(dev, C):
     out = e2c.to_cube_tensor(torch.from_numpy(frames).to(dev), layout="NHWC").cpu().numpy()
     for b in range(B):
         np.testing.assert_array_equal(out[6 * b:6 * b + 6], oe2c.to_cube(frames[b], sx, sy))
+
+
+@pytest.mark.parametrize("B,H,W,w", [(6, 96, 192, 24), (9, 50, 100, 20), (5, 66, 132, 16)])
+def test_e2c_c3_frame_groups(dev, B, H, W, w):
+    """C == 3 vector kernel: several frames per thread, frame groups, the guarded tail of the last
+    frame, and row pitches that are / are not 16 B multiples (the latter takes the scalar kernel)."""
+    frames = np.random.default_rng(B * 1000 + W).random((B, H, W, 3), dtype=np.float32)
+    e2c = cp360_b200.Equi2Cube(w, frames[0])
+    sx, sy = oe2c.fixed_maps(w, H, W)
+    for layout in ("NCHW", "NHWC"):
+        out = e2c.to_cube_tensor(torch.from_numpy(frames).to(dev), layout=layout)
+        out = (out.permute(0, 2, 3, 1) if layout == "NCHW" else out).cpu().numpy()
+        for b in range(B):
+            np.testing.assert_array_equal(out[6 * b:6 * b + 6], oe2c.to_cube(frames[b], sx, sy))
 
 
 def test_e2c_fused_norm(dev):
