@@ -455,6 +455,11 @@ static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* 
   kmax = std::min(kmax, C);
   kmax -= kmax % kq;
   if (kmax < kq) kmax = kq;
+  {                                                            // largest power of two <= kmax that respects kq: the
+    int p2 = 1;                                                // unrolled instantiations exist for those depths
+    while (p2 * 2 <= kmax) p2 *= 2;
+    if (p2 % kq == 0) kmax = p2;
+  }
   if ((int64_t)6 * kmax * HW > 65535) return false;            // 16-bit staged source offsets
   const int stages = std::min(kCubeMaxStages, std::max(2, knob("CP360_CUBE_STAGES", t_tune ? t_tune->cube_stages : 0, 3)));
   a->C = C; a->kmax = kmax; a->cblocks = (C + kmax - 1) / kmax; a->stages = stages;
@@ -477,13 +482,34 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
                   "cube-tile kernel does not apply to H=%d C=%d", g.H, C);
   a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
   smem = exclusive_smem(smem, per_sm);
-  CP360_CUDA_OK(cudaFuncSetAttribute(cubepad_cube2_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // compile-time geometry / chunk depth for the shapes of the cubic ResNet-50 and ConvLSTM sites
+  void (*kern)(const Cube2Args, const CubePadGeom) = cubepad_cube2_kernel<0, 0, 0>;
+  const bool sym1 = g.pl == 1 && g.pr == 1 && g.pt == 1 && g.pd == 1;
+#define CP360_CUBE_CASE(HH, KK) \
+  if (sym1 && g.H == HH && a.kmax == KK) kern = cubepad_cube2_kernel<HH, 1, KK>;
+  CP360_CUBE_CASE(32, 1) CP360_CUBE_CASE(32, 2) CP360_CUBE_CASE(32, 4)
+  CP360_CUBE_CASE(28, 1) CP360_CUBE_CASE(28, 2) CP360_CUBE_CASE(28, 4)
+  CP360_CUBE_CASE(16, 4) CP360_CUBE_CASE(16, 8) CP360_CUBE_CASE(16, 16)
+  CP360_CUBE_CASE(14, 4) CP360_CUBE_CASE(14, 8) CP360_CUBE_CASE(14, 16)
+  CP360_CUBE_CASE(8, 16) CP360_CUBE_CASE(8, 32) CP360_CUBE_CASE(7, 16) CP360_CUBE_CASE(7, 32)
+#undef CP360_CUBE_CASE
+  if (kern == cubepad_cube2_kernel<0, 0, 0>) {
+    switch (a.kmax) {
+      case 1: kern = cubepad_cube2_kernel<0, 0, 1>; break;
+      case 2: kern = cubepad_cube2_kernel<0, 0, 2>; break;
+      case 4: kern = cubepad_cube2_kernel<0, 0, 4>; break;
+      case 8: kern = cubepad_cube2_kernel<0, 0, 8>; break;
+      case 16: kern = cubepad_cube2_kernel<0, 0, 16>; break;
+      case 32: kern = cubepad_cube2_kernel<0, 0, 32>; break;
+      default: break;
+    }
+  }
+  CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cons_warps = std::min(31, std::max(1, knob("CP360_CUBE_WARPS", t_tune ? t_tune->cube_warps : 0, 16)));
   a.work = acquire_work_counter(st);
   // every CTA should own at least ~2 chunks
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count() * per_sm));
-  launch_kernel(cubepad_cube2_kernel, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);
+  launch_kernel(kern, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;
 }
@@ -711,9 +737,10 @@ static std::vector<TuneCfg> tune_candidates(const CubePadGeom& g, int64_t n_face
     }
   }
   if (g.H <= 45)
-    for (int kb : {24, 48})
-      for (int stages : {3, 4})
+    for (int kb : {24, 48, 96})
+      for (int stages : {2, 3, 4})
         for (int warps : {8, 16}) {
+          if (kb == 24 && stages == 2) continue;
           TuneCfg c; c.algo = ALGO_CUBE2; c.cube_stage_kb = kb; c.cube_stages = stages; c.cube_warps = warps;
           t_tune = &c;
           const bool ok = cube2_plan(g, n_faces, C, &ca, &smem, &per_sm);

@@ -40,6 +40,10 @@ struct Cube2Args {
   int32_t ring_off;     // byte offset of the input ring
 };
 
+// TH, TP > 0: face width and (symmetric) pad known at compile time; TK > 0: kmax known at compile
+// time — plane strides become immediates and the channel walk of a full chunk is unrolled, one LDS
+// and one STG per word. TH == 0 / TK == 0: run-time geometry / chunk depth.
+template <int TH, int TP, int TK>
 __global__ void __launch_bounds__(1024)
 cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -48,10 +52,13 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   int64_t* chunk_of = reinterpret_cast<int64_t*>(empty + kCubeMaxStages); // [stages] chunk id staged there, -1: end
   uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + a.lut_off);      // [6*Ho*Wo]
   const uint32_t* ring = reinterpret_cast<const uint32_t*>(smem_raw + a.ring_off);
-  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo, n_pos = 6 * HoWo;
+  const int HW = TH ? TH * TH : g.H * g.W;
+  const int HoWo = TH ? (TH + 2 * TP) * (TH + 2 * TP) : g.Ho * g.Wo;
+  const int n_pos = 6 * HoWo;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_cons = (int)blockDim.x - 32, n_cons_warps = n_cons >> 5;
-  const int fstride = a.kmax * HW;                                        // face stride in a stage
+  const int kmax = TK ? TK : a.kmax;
+  const int fstride = kmax * HW;                                          // face stride in a stage
 
   CP360_TRACE_BEGIN(2)
   pdl_trigger();
@@ -95,8 +102,8 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
         }
         chunk_of[s] = q;
         const int64_t n = q / a.cblocks;
-        const int c0 = (int)(q - n * a.cblocks) * a.kmax;
-        const int kl = min(a.kmax, a.C - c0);
+        const int c0 = (int)(q - n * a.cblocks) * kmax;
+        const int kl = min(kmax, a.C - c0);
         const uint32_t bytes = (uint32_t)(kl * HW) * 4u;
         tma::mbar_expect_tx(&full[s], 6u * bytes);
         uint32_t* dst = const_cast<uint32_t*>(ring) + (size_t)s * a.stage_words;
@@ -128,26 +135,45 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
     if (lane == 0) CP360_TRACE_MIN(2);
 #endif
     const int64_t n = q / a.cblocks;
-    const int c0 = (int)(q - n * a.cblocks) * a.kmax;
-    const int kl = min(a.kmax, a.C - c0);
+    const int c0 = (int)(q - n * a.cblocks) * kmax;
+    const int kl = min(kmax, a.C - c0);
     const uint32_t* in_s = ring + (size_t)s * a.stage_words;
     uint32_t* __restrict__ out = a.y + ((n * 6) * a.C + c0) * HoWo;
+    if (TK > 0 && kl == TK) {
+      // full chunk: channel walk unrolled in batches of 8, strides are immediates when TH > 0
+      constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
 #pragma unroll 1
-    for (int e = ctid; e < n_pos; e += n_cons) {
-      const uint32_t l = lut[e];
-      const uint32_t* sp = in_s + (l & 0xffffu);
-      uint32_t* __restrict__ dp = out + (int64_t)(l >> 29) * CHoWo + ((l >> 16) & 0x1fffu);
-      int cc = 0;
-#pragma unroll 1
-      for (; cc + 4 <= kl; cc += 4, sp += 4 * HW, dp += 4 * HoWo) {
-        const uint32_t v0 = sp[0], v1 = sp[HW], v2 = sp[2 * HW], v3 = sp[3 * HW];
-        __stcs(dp, v0);
-        __stcs(dp + HoWo, v1);
-        __stcs(dp + 2 * HoWo, v2);
-        __stcs(dp + 3 * HoWo, v3);
+      for (int e = ctid; e < n_pos; e += n_cons) {
+        const uint32_t l = lut[e];
+        const uint32_t* sp = in_s + (l & 0xffffu);
+        uint32_t* __restrict__ dp = out + (int64_t)(l >> 29) * CHoWo + ((l >> 16) & 0x1fffu);
+#pragma unroll
+        for (int c8 = 0; c8 < TK; c8 += KB) {
+          uint32_t v[KB];
+#pragma unroll
+          for (int j = 0; j < KB; ++j) v[j] = sp[(c8 + j) * HW];
+#pragma unroll
+          for (int j = 0; j < KB; ++j) __stcs(dp + (c8 + j) * HoWo, v[j]);
+        }
       }
+    } else {
 #pragma unroll 1
-      for (; cc < kl; ++cc, sp += HW, dp += HoWo) __stcs(dp, *sp);
+      for (int e = ctid; e < n_pos; e += n_cons) {
+        const uint32_t l = lut[e];
+        const uint32_t* sp = in_s + (l & 0xffffu);
+        uint32_t* __restrict__ dp = out + (int64_t)(l >> 29) * CHoWo + ((l >> 16) & 0x1fffu);
+        int cc = 0;
+#pragma unroll 1
+        for (; cc + 4 <= kl; cc += 4, sp += 4 * HW, dp += 4 * HoWo) {
+          const uint32_t v0 = sp[0], v1 = sp[HW], v2 = sp[2 * HW], v3 = sp[3 * HW];
+          __stcs(dp, v0);
+          __stcs(dp + HoWo, v1);
+          __stcs(dp + 2 * HoWo, v2);
+          __stcs(dp + 3 * HoWo, v3);
+        }
+#pragma unroll 1
+        for (; cc < kl; ++cc, sp += HW, dp += HoWo) __stcs(dp, *sp);
+      }
     }
     __syncwarp();
     if (lane == 0) tma::mbar_arrive(&empty[s]);
