@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Run one kernel a few times (for ncu): python tools/prof_one.py cubepad C H p [algo] [B]
-                                          python tools/prof_one.py e2c w [B] | c2e w C [B] | c2emax w C [B]"""
+                                          python tools/prof_one.py e2c w [B] | c2e w C [B] | c2emax w C [B]
+The last call sits inside cudaProfilerStart/Stop: run ncu with --profile-from-start off to capture
+exactly that launch (the warm-up calls include the first-call autotuning of CubePad)."""
 import os
 import sys
 
@@ -28,16 +30,33 @@ if kind == "cubepad":
     for _ in range(3 if FLUSH is None else 5):
         flush()
         y = cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
+    torch.cuda.synchronize()
+    flush()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    y = cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 elif kind == "e2c":
     w = int(sys.argv[2]); B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
     e2c = cp360_b200.Equi2Cube(w, np.empty((960, 1920, 3), np.float32))
     fr = torch.rand(B, 960, 1920, 3, device=dev)
     for _ in range(3):
         e2c.to_cube_tensor(fr)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    e2c.to_cube_tensor(fr)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 else:
     w, C = int(sys.argv[2]), int(sys.argv[3]); B = int(sys.argv[4]) if len(sys.argv) > 4 else 16
     c2e = cp360_b200.Cube2Equi(w)
     x = torch.randn(6 * B, C, w, w, device=dev)
     for _ in range(3):
         (c2e.to_equi_max if kind == "c2emax" else c2e.to_equi_nn)(x)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    (c2e.to_equi_max if kind == "c2emax" else c2e.to_equi_nn)(x)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 torch.cuda.synchronize()
