@@ -779,11 +779,17 @@ static bool autotune(const void* x, void* y, int64_t n_faces, int C, const CubeP
     }
     return best_ms;
   };
+  for (size_t i = 0; i < cands.size(); ++i) cands[i].us = time_cfg(cands[i], 2) * 1e3f;
+  // event timing is quantised (~2 us) and noisy: re-time the front-runners with more repetitions
+  std::vector<size_t> idx(cands.size());
+  for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](size_t x_, size_t y_) { return cands[x_].us < cands[y_].us; });
   int bi = -1;
-  for (size_t i = 0; i < cands.size(); ++i) {
-    const float ms = time_cfg(cands[i], 3);
-    cands[i].us = ms * 1e3f;
-    if (ms < 1e29f && (bi < 0 || ms < cands[bi].us * 1e-3f)) bi = (int)i;
+  for (size_t r = 0; r < std::min<size_t>(4, idx.size()); ++r) {
+    TuneCfg& c = cands[idx[r]];
+    if (c.us > 1e29f) continue;
+    c.us = std::min(c.us, time_cfg(c, 5) * 1e3f);
+    if (bi < 0 || c.us < cands[bi].us) bi = (int)idx[r];
   }
   if (bi >= 0 && cands[bi].algo == ALGO_ROW) {                  // ring depth around the winner
     for (int slots : {2, 4}) {
