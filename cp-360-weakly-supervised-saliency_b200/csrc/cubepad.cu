@@ -39,10 +39,22 @@ enum CubePadAlgo { ALGO_AUTO = 0, ALGO_GENERIC = 1, ALGO_BAND_STG = 2, ALGO_BAND
 // ------------------------------------------------------------------------------------------
 // generic: any element type
 // ------------------------------------------------------------------------------------------
-template <typename T>
+// Fused variants (cp360_cubepad_fused_fwd): per-channel affine + ReLU on the way through, and/or an
+// output tensor with more channels than the input (CubePad of a channel concatenation written one
+// source at a time). Set by the C-ABI entry for the duration of one call.
+struct FusedArgs {
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int relu = 0;
+  int64_t out_C = 0, out_coff = 0;
+};
+static thread_local const FusedArgs* t_fused = nullptr;
+
+template <typename T, bool EPI>
 __global__ void __launch_bounds__(256)
 cubepad_generic_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n_planes, int C,
-                       const __grid_constant__ CubePadGeom g) {
+                       const __grid_constant__ CubePadGeom g, int64_t out_C, int64_t out_coff,
+                       const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
   pdl_trigger();
   pdl_wait();
   const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
@@ -52,12 +64,22 @@ cubepad_generic_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n_pla
     const int c = (int)(plane - nf * C);
     const int f = (int)(nf % 6);
     const T* cube = x + ((nf - f) * C + c) * HW;          // face 0 of this cube, channel c
-    T* out = y + plane * HoWo;
+    T* out = y + (nf * out_C + out_coff + c) * HoWo;
+    Epi ep = {1.0f, 0.0f, relu};
+    if (EPI) {
+      if (scale) ep.sc = __ldg(scale + c);
+      if (shift) ep.sh = __ldg(shift + c);
+    }
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HoWo; e += gridDim.x * blockDim.x) {
       const int oy = e / g.Wo, ox = e - oy * g.Wo;
       int sf;
       const int pix = cubepad_src(g, f, oy, ox, &sf);
-      out[e] = cube[sf * face_stride + pix];
+      T v = cube[sf * face_stride + pix];
+      if (EPI && sizeof(T) == 4) {
+        uint32_t u = epi_apply<EPI>(*reinterpret_cast<const uint32_t*>(&v), ep);
+        v = *reinterpret_cast<const T*>(&u);
+      }
+      out[e] = v;
     }
   }
 }
@@ -369,7 +391,14 @@ static int launch_generic(const void* x, void* y, int64_t n_planes, int C, const
                           cudaStream_t st) {
   const int HoWo = g.Ho * g.Wo;
   dim3 grid((unsigned)std::min(64, (HoWo + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
-  launch_kernel(cubepad_generic_kernel<T>, grid, 256, 0, st, (const T*)x, (T*)y, n_planes, C, g);
+  const FusedArgs* fa = t_fused;
+  const int64_t out_C = fa && fa->out_C ? fa->out_C : C, out_coff = fa ? fa->out_coff : 0;
+  if (fa && (fa->scale || fa->shift || fa->relu))
+    launch_kernel(cubepad_generic_kernel<T, true>, grid, 256, 0, st, (const T*)x, (T*)y, n_planes, C, g, out_C, out_coff,
+                  fa->scale, fa->shift, fa->relu);
+  else
+    launch_kernel(cubepad_generic_kernel<T, false>, grid, 256, 0, st, (const T*)x, (T*)y, n_planes, C, g, out_C, out_coff,
+                  (const float*)nullptr, (const float*)nullptr, 0);
   CP360_LAUNCHED();
   return CP360_OK;
 }
@@ -465,6 +494,7 @@ static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* 
   a->C = C; a->kmax = kmax; a->cblocks = (C + kmax - 1) / kmax; a->stages = stages;
   a->n_chunks = (n_faces / 6) * a->cblocks;
   a->work = nullptr;
+  a->out_C = C; a->out_coff = 0; a->scale = nullptr; a->shift = nullptr; a->relu = 0;
   a->stage_words = 6 * kmax * HW;
   a->lut_off = 3 * kCubeMaxStages * 8;
   a->ring_off = (a->lut_off + 6 * HoWo * 4 + 127) & ~127;
@@ -482,28 +512,33 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
                   "cube-tile kernel does not apply to H=%d C=%d", g.H, C);
   a.x = (const uint32_t*)x; a.y = (uint32_t*)y;
   smem = exclusive_smem(smem, per_sm);
+  bool epi = false;
+  if (const FusedArgs* fa = t_fused) {
+    if (fa->out_C) { a.out_C = (int32_t)fa->out_C; a.out_coff = (int32_t)fa->out_coff; }
+    a.scale = fa->scale; a.shift = fa->shift; a.relu = fa->relu;
+    epi = fa->scale || fa->shift || fa->relu;
+  }
   // compile-time geometry / chunk depth for the shapes of the cubic ResNet-50 and ConvLSTM sites
-  void (*kern)(const Cube2Args, const CubePadGeom) = cubepad_cube2_kernel<0, 0, 0>;
+  void (*kern)(const Cube2Args, const CubePadGeom) = nullptr;
   const bool sym1 = g.pl == 1 && g.pr == 1 && g.pt == 1 && g.pd == 1;
-#define CP360_CUBE_CASE(HH, KK) \
-  if (sym1 && g.H == HH && a.kmax == KK) kern = cubepad_cube2_kernel<HH, 1, KK>;
+#define CP360_CUBE_CASE(HH, KK)                                                                            \
+  if (sym1 && g.H == HH && a.kmax == KK)                                                                   \
+    kern = epi ? cubepad_cube2_kernel<HH, 1, KK, true> : cubepad_cube2_kernel<HH, 1, KK, false>;
   CP360_CUBE_CASE(32, 1) CP360_CUBE_CASE(32, 2) CP360_CUBE_CASE(32, 4)
   CP360_CUBE_CASE(28, 1) CP360_CUBE_CASE(28, 2) CP360_CUBE_CASE(28, 4)
   CP360_CUBE_CASE(16, 4) CP360_CUBE_CASE(16, 8) CP360_CUBE_CASE(16, 16)
   CP360_CUBE_CASE(14, 4) CP360_CUBE_CASE(14, 8) CP360_CUBE_CASE(14, 16)
   CP360_CUBE_CASE(8, 16) CP360_CUBE_CASE(8, 32) CP360_CUBE_CASE(7, 16) CP360_CUBE_CASE(7, 32)
 #undef CP360_CUBE_CASE
-  if (kern == cubepad_cube2_kernel<0, 0, 0>) {
+#define CP360_CUBE_K(KK) \
+  case KK: kern = epi ? cubepad_cube2_kernel<0, 0, KK, true> : cubepad_cube2_kernel<0, 0, KK, false>; break;
+  if (!kern) {
     switch (a.kmax) {
-      case 1: kern = cubepad_cube2_kernel<0, 0, 1>; break;
-      case 2: kern = cubepad_cube2_kernel<0, 0, 2>; break;
-      case 4: kern = cubepad_cube2_kernel<0, 0, 4>; break;
-      case 8: kern = cubepad_cube2_kernel<0, 0, 8>; break;
-      case 16: kern = cubepad_cube2_kernel<0, 0, 16>; break;
-      case 32: kern = cubepad_cube2_kernel<0, 0, 32>; break;
-      default: break;
+      CP360_CUBE_K(1) CP360_CUBE_K(2) CP360_CUBE_K(4) CP360_CUBE_K(8) CP360_CUBE_K(16) CP360_CUBE_K(32)
+      default: kern = epi ? cubepad_cube2_kernel<0, 0, 0, true> : cubepad_cube2_kernel<0, 0, 0, false>; break;
     }
   }
+#undef CP360_CUBE_K
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cons_warps = std::min(31, std::max(1, knob("CP360_CUBE_WARPS", t_tune ? t_tune->cube_warps : 0, 16)));
   a.work = acquire_work_counter(st);
@@ -598,6 +633,7 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
   if (a->order != 0 && a->order != 2 && a->order != 3) a->order = 4;
   a->draw = std::min(16, std::max(1, env_int("CP360_ROW_DRAW", 2)));
   a->work = nullptr;
+  a->out_C = C; a->out_coff = 0; a->scale = nullptr; a->shift = nullptr; a->relu = 0;
   // the dynamic order hands out k = 0, 1, 2, ... per CTA and maps it to (k / 8) * warps_in_grid + ...
   if ((int64_t)a->n_units + (int64_t)sm_count() * kRowWarps * 64 * 16 > 0x7fffffff) return false;
   a->d_upp = make_fastdiv((uint32_t)a->upp);
@@ -621,17 +657,20 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   a.slot_words = (a.slot_words + slot_align - 1) / slot_align * slot_align;
   const size_t smem = (size_t)a.ring_off + (size_t)kRowWarps * a.slots * a.slot_words * 4;
   CP360_CHECK_ARG(smem <= 220 * 1024, CP360_ERR_SHAPE, "row kernel tile too large");
-  void (*kern)(const RowArgs, const CubePadGeom) = cubepad_row_kernel<0, false>;
+  bool epi = false;
+  if (const FusedArgs* fa = t_fused) {
+    if (fa->out_C) { a.out_C = (int32_t)fa->out_C; a.out_coff = (int32_t)fa->out_coff; }
+    a.scale = fa->scale; a.shift = fa->shift; a.relu = fa->relu;
+    epi = fa->scale || fa->shift || fa->relu;
+  }
   const int nj = (g.W + 31) / 32;
   const bool full = g.W % 32 == 0;
-  switch (nj) {
-    case 1: kern = full ? cubepad_row_kernel<1, true> : cubepad_row_kernel<1, false>; break;
-    case 2: kern = full ? cubepad_row_kernel<2, true> : cubepad_row_kernel<2, false>; break;
-    case 4: kern = full ? cubepad_row_kernel<4, true> : cubepad_row_kernel<4, false>; break;
-    case 7: if (!full) kern = cubepad_row_kernel<7, false>; break;
-    case 8: if (full) kern = cubepad_row_kernel<8, true>; break;
-    default: break;
-  }
+  void (*kern)(const RowArgs, const CubePadGeom) = epi ? cubepad_row_kernel<0, false, true> : cubepad_row_kernel<0, false, false>;
+#define CP360_ROW_CASE(NJ_, FULL_) \
+  if (nj == NJ_ && full == FULL_) kern = epi ? cubepad_row_kernel<NJ_, FULL_, true> : cubepad_row_kernel<NJ_, FULL_, false>;
+  CP360_ROW_CASE(1, true) CP360_ROW_CASE(1, false) CP360_ROW_CASE(2, true) CP360_ROW_CASE(2, false)
+  CP360_ROW_CASE(4, true) CP360_ROW_CASE(4, false) CP360_ROW_CASE(7, false) CP360_ROW_CASE(8, true)
+#undef CP360_ROW_CASE
   int per_sm = std::max(1, std::min(2048 / kRowThreads, (int)((224 * 1024) / (smem + 1024))));
   per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 1)));
   const size_t smem_req = exclusive_smem(smem, per_sm);
@@ -905,13 +944,14 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
     const TuneKey key = tune_key(g, n_faces, (int)C);
     TuneCfg cfg;
     if (tuned_lookup(key, &cfg)) return run_cfg(cfg, x, y, n_faces, (int)C, g, st);
-    if (autotune_allowed(n_faces, (int)C, g, st) && autotune(x, y, n_faces, (int)C, g, st, &cfg)) {
+    if (!t_fused && autotune_allowed(n_faces, (int)C, g, st) && autotune(x, y, n_faces, (int)C, g, st, &cfg)) {
       std::lock_guard<std::mutex> lock(g_tuned_mutex);
       g_tuned[key] = cfg;
       return CP360_OK;
     }
   }
   if (algo == ALGO_AUTO) algo = pick_algo(g, n_faces, (int)C, fast_ok);
+  if (t_fused && (algo == ALGO_CUBE || algo == ALGO_BAND_STG || algo == ALGO_BAND_BULK)) algo = ALGO_GENERIC;
   switch (algo) {
     case ALGO_CUBE:
       CP360_CHECK_ARG(fast_ok, CP360_ERR_ALIGN, "cube-tile kernel needs 4-byte elements, 16 B aligned");
@@ -943,6 +983,23 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
 int cp360_cubepad_fwd(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
                       int pr, int pt, int pd, int elem_bytes, void* stream) {
   return cp360_cubepad_fwd_algo(x, y, n_faces, C, H, W, pl, pr, pt, pd, elem_bytes, ALGO_AUTO, stream);
+}
+
+int cp360_cubepad_fused_fwd(const float* x, float* y, int64_t n_faces, int64_t C, int H, int W, int pl, int pr,
+                            int pt, int pd, const float* scale_dev, const float* shift_dev, int relu,
+                            int64_t out_C, int64_t out_c_off, void* stream) {
+  CP360_CHECK_ARG(out_C == 0 || (out_C >= C && out_c_off >= 0 && out_c_off + C <= out_C), CP360_ERR_BAD_ARG,
+                  "output channel window [%lld, %lld) does not fit %lld output channels", (long long)out_c_off,
+                  (long long)(out_c_off + C), (long long)out_C);
+  CP360_CHECK_ARG(out_C != 0 || out_c_off == 0, CP360_ERR_BAD_ARG, "out_c_off needs out_C");
+  CP360_CHECK_ARG(out_C <= 0x7fffffff, CP360_ERR_RANGE, "too many output channels");
+  FusedArgs fa;
+  fa.scale = scale_dev; fa.shift = shift_dev; fa.relu = relu != 0; fa.out_C = out_C; fa.out_coff = out_c_off;
+  t_fused = &fa;
+  // the plain entry's cached tiling is reused; tuning itself only happens through cp360_cubepad_fwd
+  const int rc = cp360_cubepad_fwd_algo(x, y, n_faces, C, H, W, pl, pr, pt, pd, 4, ALGO_AUTO, stream);
+  t_fused = nullptr;
+  return rc;
 }
 
 int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C, int H, int W,

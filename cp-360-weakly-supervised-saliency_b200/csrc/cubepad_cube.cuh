@@ -32,6 +32,10 @@ struct Cube2Args {
   uint32_t* work;       // {next chunk, finished CTAs} (zero at launch) or nullptr: chunks dealt round-robin
   int64_t n_chunks;     // N * cblocks
   int32_t C;
+  int32_t out_C, out_coff;   // output plane of (face-in-batch nf, channel c): nf * out_C + out_coff + c
+  const float* scale;        // EPI kernels: per-channel affine (+ ReLU) fused into the copy, see cubepad_row.cuh
+  const float* shift;
+  int32_t relu;
   int32_t kmax;         // channels per chunk (multiple of the bulk-copy channel quantum)
   int32_t cblocks;      // chunks per cube = ceil(C / kmax)
   int32_t stages;
@@ -43,7 +47,7 @@ struct Cube2Args {
 // TH, TP > 0: face width and (symmetric) pad known at compile time; TK > 0: kmax known at compile
 // time — plane strides become immediates and the channel walk of a full chunk is unrolled, one LDS
 // and one STG per word. TH == 0 / TK == 0: run-time geometry / chunk depth.
-template <int TH, int TP, int TK>
+template <int TH, int TP, int TK, bool EPI>
 __global__ void __launch_bounds__(1024)
 cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -124,7 +128,7 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
 
   // ---------------- consumers
   const int ctid = tid - 32;
-  const int64_t CHoWo = (int64_t)a.C * HoWo;
+  const int64_t CHoWo = (int64_t)a.out_C * HoWo;
   int s = 0;
   uint32_t ph = 0;
   while (true) {
@@ -138,7 +142,13 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
     const int c0 = (int)(q - n * a.cblocks) * kmax;
     const int kl = min(kmax, a.C - c0);
     const uint32_t* in_s = ring + (size_t)s * a.stage_words;
-    uint32_t* __restrict__ out = a.y + ((n * 6) * a.C + c0) * HoWo;
+    uint32_t* __restrict__ out = a.y + ((n * 6) * a.out_C + a.out_coff + c0) * HoWo;
+    const float* sc_p = (EPI && a.scale) ? a.scale + c0 : nullptr;       // L1-resident after the first position
+    const float* sh_p = (EPI && a.shift) ? a.shift + c0 : nullptr;
+    auto epi = [&](uint32_t v, int cc) -> uint32_t {
+      Epi ep = {sc_p ? __ldg(sc_p + cc) : 1.0f, sh_p ? __ldg(sh_p + cc) : 0.0f, a.relu};
+      return epi_apply<EPI>(v, ep);
+    };
     if (TK > 0 && kl == TK) {
       // full chunk: channel walk unrolled in batches of 8, strides are immediates when TH > 0
       constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
@@ -153,7 +163,7 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
 #pragma unroll
           for (int j = 0; j < KB; ++j) v[j] = sp[(c8 + j) * HW];
 #pragma unroll
-          for (int j = 0; j < KB; ++j) __stcs(dp + (c8 + j) * HoWo, v[j]);
+          for (int j = 0; j < KB; ++j) __stcs(dp + (c8 + j) * HoWo, EPI ? epi(v[j], c8 + j) : v[j]);
         }
       }
     } else {
@@ -166,13 +176,13 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
 #pragma unroll 1
         for (; cc + 4 <= kl; cc += 4, sp += 4 * HW, dp += 4 * HoWo) {
           const uint32_t v0 = sp[0], v1 = sp[HW], v2 = sp[2 * HW], v3 = sp[3 * HW];
-          __stcs(dp, v0);
-          __stcs(dp + HoWo, v1);
-          __stcs(dp + 2 * HoWo, v2);
-          __stcs(dp + 3 * HoWo, v3);
+          __stcs(dp, EPI ? epi(v0, cc) : v0);
+          __stcs(dp + HoWo, EPI ? epi(v1, cc + 1) : v1);
+          __stcs(dp + 2 * HoWo, EPI ? epi(v2, cc + 2) : v2);
+          __stcs(dp + 3 * HoWo, EPI ? epi(v3, cc + 3) : v3);
         }
 #pragma unroll 1
-        for (; cc < kl; ++cc, sp += HW, dp += HoWo) __stcs(dp, *sp);
+        for (; cc < kl; ++cc, sp += HW, dp += HoWo) __stcs(dp, EPI ? epi(*sp, cc) : *sp);
       }
     }
     __syncwarp();

@@ -32,6 +32,19 @@ namespace cp360 {
 #define CP360_ROW_ST(ptr, v) __stcs((ptr), (v))   // streaming store: the output is not re-read here
 #endif
 
+// Optional per-channel epilogue fused into the copy (fp32 tensors): v -> act(v * scale[c] + shift[c]),
+// the eval-mode BatchNorm affine + ReLU that precedes CubePad in the cubic ResNet
+// (model/resnet_cubic.py:89-92). Separate multiply and add, so a numpy fp32 restatement is bit-exact.
+struct Epi { float sc, sh; int relu; };
+
+template <bool EPI>
+__device__ __forceinline__ uint32_t epi_apply(uint32_t v, const Epi& e) {
+  if (!EPI) return v;
+  float f = __fadd_rn(__fmul_rn(__uint_as_float(v), e.sc), e.sh);
+  if (e.relu) f = f < 0.0f ? 0.0f : f;               // NaN stays NaN, like torch.relu / np.maximum
+  return __float_as_uint(f);
+}
+
 constexpr int kRowWarps = 8;
 constexpr int kRowThreads = kRowWarps * 32;
 constexpr int kRowMaxSlots = 8;
@@ -77,6 +90,13 @@ struct RowArgs {
                             //    draw groups of 8 consecutive units from the grid-wide counter, their warps draw
                             //    from the CTA's current group
   int32_t draw;
+  // output tensor may have more channels than the input (CubePad of a channel-concatenation, written
+  // one source at a time: model/clstm.py:57-58): output plane of (face-in-batch nf, channel c) is
+  // nf * out_C + out_coff + c
+  int32_t out_C, out_coff;
+  const float* scale;       // EPI kernels: [C] device, may be nullptr (1) / shift nullptr (0)
+  const float* shift;
+  int32_t relu;
   uint32_t* work;           // order 3: {next unit, finished CTAs}, zero at launch, zeroed again by the last CTA
   FastDiv d_upp, d_C;
 };
@@ -113,12 +133,12 @@ __device__ __forceinline__ uint32_t push_range(const PushEntry& pe, int ya, int 
 
 // nr rows of W words: sp (shared, row pitch W) -> dp (global, row pitch Wo); both already
 // offset by the lane. NJ = ceil(W / 32) at compile time (0: run-time loop); FULL: W % 32 == 0.
-template <int NJ, bool FULL>
+template <int NJ, bool FULL, bool EPI>
 __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32_t* __restrict__ dp,
-                                         int nr, int W, int Wo, int lane) {
+                                         int nr, int W, int Wo, int lane, const Epi& ep) {
   if (NJ == 0) {
     for (int r = 0; r < nr; ++r, sp += W, dp += Wo)
-      for (int jj = 0; jj + lane < W; jj += 32) CP360_ROW_ST(dp + jj, sp[jj]);
+      for (int jj = 0; jj + lane < W; jj += 32) CP360_ROW_ST(dp + jj, epi_apply<EPI>(sp[jj], ep));
     return;
   }
   constexpr int NJc = NJ > 0 ? NJ : 1;
@@ -133,7 +153,7 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
         if (j < NJc - 1 || tail_ok) v[j] = sp[j * 32];
 #pragma unroll
       for (int j = 0; j < NJc; ++j)
-        if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + j * 32, v[j]);
+        if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + j * 32, epi_apply<EPI>(v[j], ep));
     }
   } else {
     // narrow rows: four rows per step
@@ -150,18 +170,18 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int j = 0; j < NJc; ++j)
-          if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + k * Wo + j * 32, v[k][j]);
+          if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + k * Wo + j * 32, epi_apply<EPI>(v[k][j], ep));
     }
 #pragma unroll 1
     for (; r < nr; ++r, sp += W, dp += Wo) {
 #pragma unroll
       for (int j = 0; j < NJc; ++j)
-        if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + j * 32, sp[j * 32]);
+        if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + j * 32, epi_apply<EPI>(sp[j * 32], ep));
     }
   }
 }
 
-template <int NJ, bool FULL>
+template <int NJ, bool FULL, bool EPI>
 __global__ void __launch_bounds__(kRowThreads)
 cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -296,10 +316,15 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
 #pragma unroll 1
     for (int j = 0; j < np; ++j) {
       const uint32_t* band = in_s + j * HW;                           // row ya of this plane
-      uint32_t* __restrict__ outp = a.y + (int64_t)(plane0 + j) * HoWo;
+      uint32_t* __restrict__ outp = a.y + ((int64_t)nf * a.out_C + a.out_coff + c) * HoWo;
+      Epi ep = {1.0f, 0.0f, a.relu};
+      if (EPI) {
+        if (a.scale) ep.sc = __ldg(a.scale + c);
+        if (a.shift) ep.sh = __ldg(a.shift + c);
+      }
 
       // ---- A. interior rows: shifted copy shared -> global
-      row_copy<NJ, FULL>(band + lane, outp + (ya + g.pt) * Wo + g.pl + lane, yb - ya, W, Wo, lane);
+      row_copy<NJ, FULL, EPI>(band + lane, outp + (ya + g.pt) * Wo + g.pl + lane, yb - ya, W, Wo, lane, ep);
 
       // ---- B. push: halo elements of other faces' planes (same cube, same channel) whose source
       //         pixel lies in rows [ya, yb) of this plane
@@ -316,7 +341,7 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
         if (pe.drive == 0 && pe.V >= 16 && wd[e] > 0) {
           // whole plate rows (top / down plates fed by the first / last rows of a face): a row
           // copy with an optional reversal and clamped ends, lanes along the row
-          uint32_t* __restrict__ dface = a.y + ((int64_t)(nf - f + pe.dface) * a.C + c) * HoWo;
+          uint32_t* __restrict__ dface = a.y + ((int64_t)(nf - f + pe.dface) * a.out_C + a.out_coff + c) * HoWo;
 #pragma unroll 1
           for (int u = i0; u < i0 + wd[e]; ++u) {
             const int r = pe.cmode ? min(max(u + pe.off, 0), H - 1) : u;
@@ -325,14 +350,14 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
 #pragma unroll 1
             for (int v = lane; v < pe.V; v += 32) {
               const int cc = pe.cmode ? v : min(max(v + pe.off, 0), W - 1);
-              CP360_ROW_ST(drow + v, srow[pe.xc * cc]);
+              CP360_ROW_ST(drow + v, epi_apply<EPI>(srow[pe.xc * cc], ep));
             }
           }
           cnt[e] = 0;
         }
       }
       const int c1 = cnt[0], c2 = c1 + cnt[1], c3 = c2 + cnt[2], n_push = c3 + cnt[3];
-      uint32_t* __restrict__ cube_out = a.y + ((int64_t)(nf - f) * a.C + c) * HoWo;
+      uint32_t* __restrict__ cube_out = a.y + ((int64_t)(nf - f) * a.out_C + a.out_coff + c) * HoWo;
 #pragma unroll 1
       for (int q = lane; q < n_push; q += 32) {
         const int e = (q >= c1) + (q >= c2) + (q >= c3);
@@ -349,8 +374,8 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
         const int r = pe.cmode ? min(max(u + pe.off, 0), H - 1) : u;
         const int cc = pe.cmode ? v : min(max(v + pe.off, 0), W - 1);
         const int yy = pe.yr * r + pe.yc * cc + pe.y0, xx = pe.xr * r + pe.xc * cc + pe.x0;
-        CP360_ROW_ST(cube_out + (int64_t)pe.dface * a.C * HoWo + (pe.oy0 + u) * Wo + pe.ox0 + v,
-                     band[(yy - ya) * W + xx]);
+        CP360_ROW_ST(cube_out + (int64_t)pe.dface * a.out_C * HoWo + (pe.oy0 + u) * Wo + pe.ox0 + v,
+                     epi_apply<EPI>(band[(yy - ya) * W + xx], ep));
       }
       if (np > 1 && ++c == a.C) { c = 0; ++nf; if (++f == 6) f = 0; }
     }

@@ -67,6 +67,72 @@ def cubepad_forward(x, pads, algo=_lib.ALGO_AUTO):
     return y
 
 
+def cubepad_fused(x, pads, scale=None, shift=None, relu=False, out=None, out_channel_offset=0):
+    """CubePad(act(x * scale[c] + shift[c])) in ONE pass (fp32): the eval-mode BatchNorm affine and
+    ReLU that precede CubePad in the cubic ResNet (model/resnet_cubic.py:89-92) never cost a tensor
+    round trip of their own. `out` [6N,Cout,Ho,Wo] with Cout >= C lets several sources land in one
+    padded tensor (see cubepad_cat). Separate multiply and add: bit-exact against numpy fp32."""
+    _require_cuda(x, "cubepad_fused")
+    if x.dim() != 4 or x.dtype != torch.float32:
+        raise ValueError("cubepad_fused expects a float32 [6N, C, H, W] tensor")
+    p_l, p_r, p_t, p_d = pads
+    n, c, h, w = x.shape
+    if n % 6 != 0:
+        raise ValueError("CubePad size mismatch! batch %d is not a multiple of 6" % n)
+    x = x.contiguous()
+    ho, wo = h + p_t + p_d, w + p_l + p_r
+    if out is None:
+        if out_channel_offset:
+            raise ValueError("out_channel_offset needs out")
+        out = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device)
+    if (out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device or out.dim() != 4 or
+            out.shape[0] != n or out.shape[2] != ho or out.shape[3] != wo):
+        raise ValueError("out must be a contiguous float32 [%d, Cout, %d, %d] tensor on %s" % (n, ho, wo, x.device))
+
+    def vec(v, name):
+        if v is None:
+            return None
+        v = torch.as_tensor(v, dtype=torch.float32, device=x.device).contiguous()
+        if v.numel() != c:
+            raise ValueError("%s needs %d entries, got %d" % (name, c, v.numel()))
+        return v
+    scale, shift = vec(scale, "scale"), vec(shift, "shift")
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().cp360_cubepad_fused_fwd(
+            x.data_ptr(), out.data_ptr(), n, c, h, w, p_l, p_r, p_t, p_d,
+            scale.data_ptr() if scale is not None else None, shift.data_ptr() if shift is not None else None,
+            int(bool(relu)), out.shape[1], int(out_channel_offset), st))
+    return out
+
+
+def cubepad_cat(tensors, lrtd_pad):
+    """CubePad(torch.cat(tensors, 1)) without materialising the concatenation (model/clstm.py:57-58):
+    every source is read once and written straight into its channel window of the padded tensor."""
+    pads = get_pad_size(lrtd_pad)
+    p_l, p_r, p_t, p_d = pads
+    n, _, h, w = tensors[0].shape
+    ctot = sum(int(t.shape[1]) for t in tensors)
+    out = torch.empty((n, ctot, h + p_t + p_d, w + p_l + p_r), dtype=torch.float32, device=tensors[0].device)
+    off = 0
+    for t in tensors:
+        if t.shape[0] != n or t.shape[2] != h or t.shape[3] != w:
+            raise ValueError("cubepad_cat: tensors must agree in every dimension but channels")
+        cubepad_fused(t, pads, out=out, out_channel_offset=off)
+        off += int(t.shape[1])
+    return out
+
+
+def cubepad_bn_relu(x, bn, lrtd_pad, relu=True):
+    """CubePad(relu(bn(x))) for an eval-mode nn.BatchNorm2d, folded into the pad kernel's epilogue."""
+    if bn.training or bn.running_mean is None:
+        raise ValueError("cubepad_bn_relu folds running statistics: call bn.eval() first")
+    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+    scale = inv * (bn.weight.float() if bn.affine else 1.0)
+    shift = (bn.bias.float() if bn.affine else 0.0) - bn.running_mean.float() * scale
+    return cubepad_fused(x, get_pad_size(lrtd_pad), scale=scale, shift=shift, relu=relu)
+
+
 def cubepad_backward(gy, pads, in_hw):
     _require_cuda(gy, "CubePad.backward")
     p_l, p_r, p_t, p_d = pads

@@ -92,6 +92,15 @@ CP360_API int cp360_cubepad_fwd_algo(const void* x_dev, void* y_dev, int64_t n_f
 CP360_API int cp360_cubepad_pick_algo(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt,
                             int pd, int elem_bytes, int aligned16);
 
+/* Device, fp32: y = CubePad(act(x * scale[c] + shift[c])) in one pass — the eval-mode BatchNorm affine + ReLU that
+ * precede CubePad at model/resnet_cubic.py:89-92 (separate multiply and add; act = ReLU if relu != 0). scale_dev /
+ * shift_dev: device float[C] or NULL (1 / 0). out_C > 0: y has out_C >= C channels and the padded planes land in
+ * channels [out_c_off, out_c_off + C) — CubePad of a channel concatenation (model/clstm.py:57-58) written one
+ * source at a time, without materialising the cat. out_C == 0: y has C channels. Same status codes as cp360_cubepad_fwd. */
+CP360_API int cp360_cubepad_fused_fwd(const float* x_dev, float* y_dev, int64_t n_faces, int64_t C, int H, int W,
+                            int pl, int pr, int pt, int pd, const float* scale_dev, const float* shift_dev,
+                            int relu, int64_t out_C, int64_t out_c_off, void* stream);
+
 /* Host: human-readable tiling the first-call autotuner chose for this problem on the current device
  * ("" if the problem has not been tuned: too small, stream was capturing, CP360_AUTOTUNE=0). */
 CP360_API int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,

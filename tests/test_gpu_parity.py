@@ -112,6 +112,67 @@ def test_cubepad_autotuned_path(dev, shape, pad, monkeypatch):
     np.testing.assert_array_equal(y2.cpu().numpy(), want)
 
 
+FUSED_SHAPES = [((6, 8, 16, 16), 1), ((12, 16, 8, 8), 1), ((6, 12, 7, 7), 1), ((6, 4, 32, 32), 1), ((12, 6, 64, 64), 1),
+                ((6, 3, 128, 128), 3), ((6, 5, 28, 28), [1, 2, 2, 1]), ((6, 3, 9, 9), 2), ((6, 64, 14, 14), 1)]
+
+
+@pytest.mark.parametrize("shape,pad", FUSED_SHAPES)
+def test_cubepad_fused_affine_relu_vs_oracle(dev, shape, pad):
+    """cp360_cubepad_fused_fwd: CubePad(relu(x * scale + shift)) — bit-exact against the numpy fp32
+    restatement (separate multiply and add), for the row, cube-tile and generic kernels."""
+    rng = np.random.default_rng(zlib.crc32(repr((shape, pad, "fused")).encode()))
+    x = rng.standard_normal(shape).astype(np.float32)
+    C = shape[1]
+    scale = rng.uniform(0.5, 2.0, C).astype(np.float32)
+    shift = rng.standard_normal(C).astype(np.float32)
+    pads = cp360_b200.get_pad_size(pad)
+    xt = torch.from_numpy(x).to(dev)
+    pre = x * scale.reshape(1, C, 1, 1) + shift.reshape(1, C, 1, 1)
+    for relu, sc, sh in ((True, scale, shift), (False, scale, shift), (True, None, None), (False, None, shift)):
+        want = x.copy()
+        if sc is not None:
+            want = want * sc.reshape(1, C, 1, 1)
+        if sh is not None:
+            want = (want + sh.reshape(1, C, 1, 1)).astype(np.float32)
+        if relu:
+            want = np.maximum(want, np.float32(0))
+        got = cp360_b200.cubepad_fused(xt, pads, scale=None if sc is None else torch.from_numpy(sc),
+                                       shift=None if sh is None else torch.from_numpy(sh), relu=relu)
+        np.testing.assert_array_equal(got.cpu().numpy(), ocp.cubepad(want.astype(np.float32), pad))
+    assert pre.dtype == np.float32
+
+
+@pytest.mark.parametrize("shape,pad", FUSED_SHAPES)
+def test_cubepad_cat_vs_oracle(dev, shape, pad):
+    """CubePad of a channel concatenation written one source at a time (model/clstm.py:57-58)."""
+    rng = np.random.default_rng(zlib.crc32(repr((shape, pad, "cat")).encode()))
+    n, c, h, w = shape
+    parts = [rng.standard_normal((n, ci, h, w)).astype(np.float32) for ci in (c, 2 * c, c)]
+    want = ocp.cubepad(np.concatenate(parts, axis=1), pad)
+    got = cp360_b200.cubepad_cat([torch.from_numpy(p).to(dev) for p in parts], pad)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    with pytest.raises(_lib.CP360Error):
+        cp360_b200.cubepad_fused(torch.from_numpy(parts[0]).to(dev), cp360_b200.get_pad_size(pad),
+                                 out=got, out_channel_offset=3 * c + 1)
+
+
+def test_cubepad_bn_relu_matches_torch(dev):
+    """The call-site pattern of model/resnet_cubic.py:89-92 (bn -> relu -> pad) against torch's own ops."""
+    torch.manual_seed(0)
+    for (n, c, h) in ((6, 64, 64), (12, 256, 16), (6, 128, 32)):
+        bn = torch.nn.BatchNorm2d(c).to(dev)
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+        bn.eval()
+        x = torch.randn(n, c, h, h, device=dev)
+        with torch.no_grad():
+            want = cp360_b200.CubePad(1)(torch.relu(bn(x)))
+        got = cp360_b200.cubepad_bn_relu(x, bn, 1)
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        cp360_b200.cubepad_bn_relu(x, torch.nn.BatchNorm2d(c).to(dev), 1)      # training mode
+
+
 @pytest.mark.parametrize("dtype", [torch.uint8, torch.float16, torch.bfloat16, torch.float64, torch.int64,
                                    torch.complex128])
 def test_cubepad_any_dtype(dev, dtype):

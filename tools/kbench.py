@@ -90,6 +90,27 @@ def main():
                        timeit(fn, args.iters, flush))
             del x
 
+    if args.only in ("", "fused"):
+        # rows (f2) of SURVEY.md section 8: producer ops folded into the pad kernel, next to the unfused sequence
+        for C, H in ((64, 128), (256, 32), (512, 16)):
+            n = 6 * B
+            x = torch.randn(n, C, H, H, device=dev)
+            bn = torch.nn.BatchNorm2d(C).to(dev).eval()
+            pad = cp360_b200.CubePad(1)
+            nbytes = n * C * (H * H + (H + 2) ** 2) * 4
+            with torch.no_grad():
+                report("bn+relu+CubePad [%d,%d,%d,%d] torch bn, relu + cp360 pad" % (n, C, H, H), nbytes,
+                       timeit(lambda: pad(torch.relu(bn(x))), args.iters, flush))
+                report("bn+relu+CubePad [%d,%d,%d,%d] fused (cp360_cubepad_fused_fwd)" % (n, C, H, H), nbytes,
+                       timeit(lambda: cp360_b200.cubepad_bn_relu(x, bn, 1), args.iters, flush))
+                xs = [x, torch.randn(n, C, H, H, device=dev)]
+                nb2 = 2 * nbytes
+                report("cat+CubePad     2x[%d,%d,%d,%d] torch.cat + cp360 pad" % (n, C, H, H), nb2,
+                       timeit(lambda: pad(torch.cat(xs, 1)), args.iters, flush))
+                report("cat+CubePad     2x[%d,%d,%d,%d] fused (2 windowed launches)" % (n, C, H, H), nb2,
+                       timeit(lambda: cp360_b200.cubepad_cat(xs, 1), args.iters, flush))
+            del x, xs
+
     if args.only in ("", "e2c"):
         pipe = cp360_b200.SphericalPipeline(device=dev)
         for w in (256, 224):
