@@ -6,6 +6,8 @@ A numpy restatement of the reference algorithms
   oracle.cubepad   model/cube_pad.py:23-216            (CubePad index map + apply)
   oracle.e2c       utils/equi_to_cube.py:12-129        (Equi2Cube maps, cv2 fixed-point bilinear)
   oracle.c2e       utils/cube_to_equi.py:12-66         (Cube2Equi maps, single-pass grid_sample)
+  oracle.cam       static_model/class_activation_model.py:46-52,76-90 (CAM contraction, heat-map post-ops;
+                   pinned by tests/golden/make_golden_cam.py -> golden_cam.npz)
   oracle.ref_port  the same three ops re-expressed with the library calls the reference
                    itself makes (cv2.remap, torch.cat/flip, F.grid_sample) — CPU baseline
                    arm of bench.py only.
