@@ -12,6 +12,7 @@
 //   c2e_small_kernel w <= 16: the 6 faces of a channel group are staged in shared memory by TMA
 //                    bulk copies; used by both variants
 //   c2e_bwd_kernel   bilinear scatter-add of the output gradient (training path)
+//   c2e_cubic_*      Cube2Equi.to_equi_cv2 (cube_to_equi.py:68-91): cv2.remap(INTER_CUBIC) arithmetic
 #include <algorithm>
 
 #include "common.cuh"
@@ -172,6 +173,134 @@ c2e_bwd_kernel(const float* __restrict__ gequi, const uint32_t* __restrict__ tap
   }
 }
 
+// ---- bicubic variant: Cube2Equi.to_equi_cv2 (utils/cube_to_equi.py:68-91) ---------------------
+// cv2.remap(INTER_CUBIC) semantics for float sources (OpenCV remapBicubic): 1/32-pixel fractions
+// select rows of the A = -0.75 coefficient table, the 4x4 weight is fl(wy[i]*wx[j]); a window that
+// lies fully inside the face is summed row by row ((S0*w0 + S1*w1) + S2*w2) + S3*w3, any other
+// window tap by tap with the taps outside the face skipped (BORDER_CONSTANT 0). fp32, no FMA —
+// the result is bit-identical to cv2's.
+struct CubicTap {
+  int face, y0, x0, fx, fy;
+};
+
+__device__ __forceinline__ CubicTap decode_cubic_tap(uint32_t t) {
+  CubicTap r;
+  r.face = (int)(t >> 28);
+  r.fy = (int)((t >> 23) & 31u);
+  r.fx = (int)((t >> 18) & 31u);
+  r.y0 = (int)((t >> 9) & 0x1ffu) - 1;
+  r.x0 = (int)(t & 0x1ffu) - 1;
+  return r;
+}
+
+// OpenCV's interpolateCubic at x = k/32, same operation order, no contraction
+__device__ __forceinline__ void cubic_coeffs(int k, float c[4]) {
+  const float A = -0.75f;
+  const float x = __fmul_rn((float)k, 1.0f / 32);
+  const float x1 = __fadd_rn(x, 1.0f), xm = __fsub_rn(1.0f, x);
+  c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), 5.0f * A), x1), 8.0f * A), x1), 4.0f * A);
+  c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.0f, x), A + 3.0f), x), x), 1.0f);
+  c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.0f, xm), A + 3.0f), xm), xm), 1.0f);
+  c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, c[0]), c[1]), c[2]);
+}
+
+// One output pixel over `kl` channels. src = channel 0 of the pixel's face (plane stride ww),
+// dst = channel 0 of the output pixel (plane stride P).
+__device__ __forceinline__ void cubic_pixel(const float* __restrict__ src, float* __restrict__ dst,
+                                            const CubicTap t, int w, int ww, int P, int kl) {
+  float cx[4], cy[4], wt[16];
+  cubic_coeffs(t.fx, cx);
+  cubic_coeffs(t.fy, cy);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wt[i * 4 + j] = __fmul_rn(cy[i], cx[j]);
+  const int lim = max(w - 3, 0);
+  const bool inside = (unsigned)t.x0 < (unsigned)lim && (unsigned)t.y0 < (unsigned)lim;
+  if (inside) {
+    src += t.y0 * w + t.x0;
+#pragma unroll 2
+    for (int c = 0; c < kl; ++c, src += ww) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* r = src + i * w;
+        float rs = __fadd_rn(__fmul_rn(r[0], wt[i * 4]), __fmul_rn(r[1], wt[i * 4 + 1]));
+        rs = __fadd_rn(rs, __fmul_rn(r[2], wt[i * 4 + 2]));
+        rs = __fadd_rn(rs, __fmul_rn(r[3], wt[i * 4 + 3]));
+        sum = i == 0 ? rs : __fadd_rn(sum, rs);
+      }
+      __stcs(dst + (int64_t)c * P, sum);
+    }
+  } else {
+    unsigned ok = 0;
+    int off[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yy = t.y0 + i, xx = t.x0 + j;
+        const bool v = (unsigned)yy < (unsigned)w && (unsigned)xx < (unsigned)w;
+        ok |= (unsigned)v << (i * 4 + j);
+        off[i * 4 + j] = v ? yy * w + xx : 0;
+      }
+#pragma unroll 2
+    for (int c = 0; c < kl; ++c, src += ww) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (ok & (1u << k)) sum = __fadd_rn(sum, __fmul_rn(src[off[k]], wt[k]));
+      __stcs(dst + (int64_t)c * P, sum);
+    }
+  }
+}
+
+// w <= 16: same staging as c2e_small_kernel (block = (b, channel group), six bulk copies)
+__global__ void __launch_bounds__(kC2eSmallThreads)
+c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
+                       float* __restrict__ out, int C, int w, int kch, int groups) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* cs = reinterpret_cast<float*>(smem_raw + 128);       // [6][kch][w*w]
+  const int P = 8 * w * w, ww = w * w;
+  const int b = blockIdx.x / groups, gidx = blockIdx.x - b * groups;
+  const int c0 = gidx * kch, kl = min(kch, C - c0);
+  const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  if (tid == 0) {
+    tma::mbar_init(bar, 1);
+    tma::fence_mbar_init();
+    const uint32_t bytes = (uint32_t)(kl * ww) * 4u;
+    tma::mbar_expect_tx(bar, 6u * bytes);
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      tma::bulk_load(cs + (size_t)f * kch * ww, cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
+  }
+  __syncthreads();
+  tma::mbar_wait(bar, 0);
+  for (int pix = tid; pix < P; pix += kC2eSmallThreads) {
+    const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
+    cubic_pixel(cs + (size_t)t.face * kch * ww, out + ((int64_t)b * C + c0) * P + pix, t, w, ww, P, kl);
+  }
+}
+
+// any w: taps read through the read-only path (the cube of one frame is L2-resident)
+__global__ void __launch_bounds__(kC2eThreads)
+c2e_cubic_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
+                 float* __restrict__ out, int64_t B, int C, int w, int ch_per_block) {
+  pdl_trigger();
+  pdl_wait();
+  const int P = 8 * w * w, ww = w * w;
+  const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
+  if (pix >= P) return;
+  const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
+  const int c_begin = blockIdx.y * ch_per_block, kl = min(C, c_begin + ch_per_block) - c_begin;
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z)
+    cubic_pixel(cube + ((b * 6 + t.face) * C + c_begin) * (int64_t)ww,
+                out + (b * C + c_begin) * (int64_t)P + pix, t, w, ww, P, kl);
+}
+
 static int check_common(const void* a, const void* taps, const void* wts, const void* o, int64_t B,
                         int64_t C, int w) {
   CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0, CP360_ERR_BAD_ARG, "bad size");
@@ -256,6 +385,43 @@ int cp360_c2e_max_fwd(const float* cube, const uint32_t* taps, const float* wts,
   launch_kernel(fill_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st, sal, n, -INFINITY);
   CP360_LAUNCHED();
   return launch_c2e<1>(cube, taps, wts, sal, B, C, w, st);
+}
+
+int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, int64_t B, int64_t C,
+                        int w, void* stream) {
+  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0, CP360_ERR_BAD_ARG, "bad size");
+  CP360_CHECK_ARG(w <= 512 && C <= 0x7fffffff, CP360_ERR_RANGE, "face width > 512 / too many channels");
+  if (B == 0 || C == 0) return CP360_OK;
+  CP360_CHECK_ARG(cube && taps && equi, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG(((uintptr_t)cube % 4) == 0 && ((uintptr_t)equi % 4) == 0 && ((uintptr_t)taps % 4) == 0,
+                  CP360_ERR_ALIGN, "tensors must be 4 B aligned");
+  int rc = require_device();
+  if (rc != CP360_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = 8 * w * w;
+  size_t smem = 0;
+  int k = small_plan(cube, C, w, &smem);
+  if (k > 0) {
+    const int ww = w * w;
+    int q = 1;
+    while ((q * ww) % 4) q <<= 1;
+    while (k > 4 * q && B * ((C + k - 1) / k) < 2 * (int64_t)sm_count()) k = std::max(q, (k / 2) - ((k / 2) % q));
+    smem = 128 + (size_t)6 * k * ww * 4;
+    const int groups = (int)((C + k - 1) / k);
+    CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
+    CP360_CUDA_OK(cudaFuncSetAttribute(c2e_cubic_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(c2e_cubic_small_kernel, (unsigned)(B * groups), kC2eSmallThreads, smem, st, cube, taps, equi,
+                  (int)C, w, k, groups);
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
+  const int chb = (int)std::min<int64_t>(8, C);
+  dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)((C + chb - 1) / chb),
+            (unsigned)std::min<int64_t>(B, 65535));
+  CP360_CHECK_ARG(grid.y <= 65535, CP360_ERR_RANGE, "too many channel chunks");
+  launch_kernel(c2e_cubic_kernel, grid, kC2eThreads, 0, st, cube, taps, equi, B, (int)C, w, chb);
+  CP360_LAUNCHED();
+  return CP360_OK;
 }
 
 int cp360_c2e_bwd(const float* gequi, const uint32_t* taps, const float* wts, float* gcube,

@@ -242,4 +242,22 @@ int cp360_c2e_build_plan(int w, int align_corners, uint32_t* tap_host, float* wt
   return CP360_OK;
 }
 
+int cp360_c2e_build_cubic_plan(int w, uint32_t* tap_host) {
+  if (w <= 0 || !tap_host) { set_error("c2e cubic plan: bad argument"); return CP360_ERR_BAD_ARG; }
+  if (w > 512) { set_error("c2e cubic plan: face width > 512"); return CP360_ERR_RANGE; }
+  const size_t P = (size_t)8 * w * w;
+  std::vector<int8_t> face(P);
+  std::vector<double> coord(2 * P);
+  int rc = cp360_c2e_build_map(w, face.data(), coord.data());
+  if (rc != CP360_OK) return rc;
+  for (size_t i = 0; i < P; ++i) {
+    // cube_to_equi.py:83 gridf.astype(np.float32), then cv2's float map -> 1/32-pixel fixed point
+    const int32_t sx = cv_round_f32_times32(coord[2 * i]), sy = cv_round_f32_times32(coord[2 * i + 1]);
+    const uint32_t x0p1 = (uint32_t)(sx >> 5), y0p1 = (uint32_t)(sy >> 5);   // window origin + 1, in [0, w-1]
+    tap_host[i] = ((uint32_t)face[i] << 28) | ((uint32_t)(sy & 31) << 23) | ((uint32_t)(sx & 31) << 18) |
+                  (y0p1 << 9) | x0p1;
+  }
+  return CP360_OK;
+}
+
 }  // extern "C"

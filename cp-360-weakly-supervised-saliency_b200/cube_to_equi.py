@@ -1,8 +1,9 @@
-"""Cube2Equi — host mirror of the reference's utils/cube_to_equi.py:11-66.
+"""Cube2Equi — host mirror of the reference's utils/cube_to_equi.py:11-91.
 
     c2e = Cube2Equi(input_w)                   # builds face_map / out_coord (host, once)
     equi = c2e.to_equi_nn(cube)                # [6,C,w,w] -> cuda [1,C,2w,4w]     (reference API)
     sal  = c2e.to_equi_max(cube)               # [6B,C,w,w] -> [B,2w,4w] fused channel max (addition)
+    equi = c2e.to_equi_cv2(cube_numpy)         # [6,C,w,w] -> numpy [C,2w,4w], bicubic (:68-91)
 
 The unmodified reference calls F.grid_sample without ``align_corners``; under the installed
 torch (2.11) that means align_corners=False, which is therefore the default here. Pass
@@ -90,6 +91,35 @@ class Cube2Equi:
         if out is None:
             out = torch.empty((b, 2 * w, 4 * w), dtype=torch.float32, device=x.device)
         return self._launch("cp360_c2e_max_fwd", x, out, b, c)
+
+    def _cubic_plan_on(self, device):
+        key = ("cubic", device.type, device.index)
+        p = self._plan_dev.get(key)
+        if p is None:
+            taps = np.empty(8 * self.input_w * self.input_w, dtype=np.uint32)
+            _lib.check(_lib.lib().cp360_c2e_build_cubic_plan(self.input_w, taps.ctypes.data))
+            p = torch.from_numpy(taps.view(np.int32)).to(device)
+            self._plan_dev[key] = p
+        return p
+
+    def to_equi_cv2(self, input_data):
+        """Bicubic back-projection with cv2.remap(INTER_CUBIC) arithmetic (cube_to_equi.py:68-91).
+
+        numpy [6,C,w,w] -> numpy float32 [C,2w,4w] (the reference's signature; it hard-codes
+        C = 1000, here any C). A CUDA tensor [6B,C,w,w] returns a CUDA tensor [B,C,2w,4w]."""
+        as_numpy = isinstance(input_data, np.ndarray)
+        x = self._prepare(input_data)
+        b, c, w = x.shape[0] // 6, x.shape[1], self.input_w
+        taps = self._cubic_plan_on(x.device)
+        out = torch.empty((b, c, 2 * w, 4 * w), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().cp360_c2e_cubic_fwd(x.data_ptr(), taps.data_ptr(), out.data_ptr(), b, c, w, st))
+        if as_numpy:
+            if b != 1:
+                raise ValueError("numpy input is one cube [6,C,w,w] (cube_to_equi.py:68-74)")
+            return out[0].cpu().numpy()
+        return out
 
 
 class _C2EFn(torch.autograd.Function):

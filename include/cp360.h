@@ -177,6 +177,20 @@ CP360_API int cp360_c2e_fwd(const float* cube_dev, const uint32_t* tap_dev, cons
 CP360_API int cp360_c2e_max_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
                       float* sal_dev, int64_t B, int64_t C, int w, void* stream);
 
+/* Host: sampling plan of Cube2Equi.to_equi_cv2, cube_to_equi.py:68-91 — cv2.remap(INTER_CUBIC) fed
+ * float32(out_coord) as it is (face pixels, no normalisation): s = cvRound(float32(coord)*32),
+ *   tap_host[2w*4w] uint32: face<<28 | (sy&31)<<23 | (sx&31)<<18 | (sy>>5)<<9 | (sx>>5)
+ * ((s>>5)-1 is the origin of the 4x4 window, s&31 the row of OpenCV's bicubic table). w <= 512. */
+CP360_API int cp360_c2e_build_cubic_plan(int w, uint32_t* tap_host);
+
+/* Device, fp32: equi[B,C,2w,4w] from cube[6B,C,w,w] with cv2.remap(INTER_CUBIC, BORDER_CONSTANT 0)
+ * arithmetic (A = -0.75 table, 4x4 fp32 weight products, OpenCV's summation order, no FMA), each
+ * output pixel sampled from the face face_map assigns it. Replaces Cube2Equi.to_equi_cv2,
+ * cube_to_equi.py:68-91 (6 x 250 cv2.remap calls + boolean-mask scatters); any C (the reference
+ * hard-codes 1000 channels, :88). */
+CP360_API int cp360_c2e_cubic_fwd(const float* cube_dev, const uint32_t* tap_dev, float* equi_dev, int64_t B,
+                        int64_t C, int w, void* stream);
+
 /* Device, fp32: gcube[6B,C,w,w] = d(c2e)^T(gequi[B,C,2w,4w]) (bilinear scatter-add). */
 CP360_API int cp360_c2e_bwd(const float* gequi_dev, const uint32_t* tap_dev, const float* wts_dev,
                   float* gcube_dev, int64_t B, int64_t C, int w, void* stream);

@@ -100,3 +100,68 @@ def to_equi(cube, face_map, out_coord, align_corners=False):
 def to_equi_max(cube, face_map, out_coord, align_corners=False):
     """Channel max of to_equi -> [2w,4w] (test_temporal.py:82-84, train_temporal.py:105-106)."""
     return to_equi(cube, face_map, out_coord, align_corners)[0].max(axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# to_equi_cv2 — utils/cube_to_equi.py:68-91: cv2.remap(face[..., 4d:4d+4], out_coord_x, out_coord_y,
+# INTER_CUBIC) per face and channel quad, masked by face_map. Coordinates are used as they are
+# (face pixels, NOT normalised like to_equi_nn). The third-party arithmetic restated here is
+# OpenCV's remapBicubic for float sources (imgproc/src/imgwarp.cpp; installed cv2 4.13, the
+# algorithm is unchanged since 2.x):
+#   * float maps -> 1/32-pixel fixed point: s = cvRound(float32(coord) * 32); tap origin (s >> 5) - 1,
+#     fraction s & 31 picks a row of the bicubic coefficient table (A = -0.75, fp32);
+#   * the 4x4 weight is fl(wy[i] * wx[j]) (table of products, fp32);
+#   * origin with all 16 taps inside the face: sum = r0; sum += r1; sum += r2; sum += r3 with
+#     r_i = ((S0*w0 + S1*w1) + S2*w2) + S3*w3 (fp32, no FMA);
+#   * otherwise (BORDER_CONSTANT, value 0): sum = 0, then sum += S*w tap by tap in row-major order,
+#     skipping taps outside the face.
+# ------------------------------------------------------------------------------------------------
+def cubic_table():
+    """[32,4] fp32 coefficients of OpenCV's interpolateCubic at x = k/32."""
+    f = np.float32
+    x = np.arange(32, dtype=np.float32) * f(1.0 / 32)
+    A = f(-0.75)
+    x1 = x + f(1)
+    c0 = ((A * x1 - f(5) * A) * x1 + f(8) * A) * x1 - f(4) * A
+    c1 = ((A + f(2)) * x - (A + f(3))) * x * x + f(1)
+    xm = f(1) - x
+    c2 = ((A + f(2)) * xm - (A + f(3))) * xm * xm + f(1)
+    c3 = f(1) - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], axis=1).astype(np.float32)
+
+
+def cubic_plan(out_coord):
+    """(x0, y0, fx, fy) int32 [2w,4w]: tap origin (top-left of the 4x4 window) and 1/32 fractions."""
+    g = np.asarray(out_coord).astype(np.float32)
+    s = np.rint(g.astype(np.float64) * 32).astype(np.int64)      # cvRound: round half to even
+    sx, sy = s[..., 0], s[..., 1]
+    return ((sx >> 5) - 1).astype(np.int32), ((sy >> 5) - 1).astype(np.int32), \
+        (sx & 31).astype(np.int32), (sy & 31).astype(np.int32)
+
+
+def to_equi_cv2(cube, face_map, out_coord):
+    """cube [6,C,w,w] fp32 -> [C,2w,4w] fp32 (bicubic, zeros outside the face)."""
+    cube = np.asarray(cube, dtype=np.float32)
+    _, C, w, _ = cube.shape
+    x0, y0, fx, fy = cubic_plan(out_coord)
+    tab = cubic_table()
+    wx, wy = tab[fx], tab[fy]                                   # [2w,4w,4]
+    f = np.asarray(face_map).astype(np.int64)
+    lim = max(w - 3, 0)
+    inside = (x0 >= 0) & (x0 < lim) & (y0 >= 0) & (y0 < lim)
+    zero = np.float32(0)
+    acc_in = None                                               # all-taps-inside order
+    acc_bd = np.zeros((C,) + f.shape, dtype=np.float32)         # border order
+    for i in range(4):
+        row = None
+        yy = y0 + i
+        for j in range(4):
+            xx = x0 + j
+            ok = (yy >= 0) & (yy < w) & (xx >= 0) & (xx < w)
+            v = cube[f, :, np.clip(yy, 0, w - 1), np.clip(xx, 0, w - 1)]          # [2w,4w,C]
+            wt = (wy[..., i] * wx[..., j]).astype(np.float32)
+            p = np.transpose(v * wt[..., None], (2, 0, 1))
+            row = p if row is None else row + p
+            acc_bd = np.where(ok[None], acc_bd + p, acc_bd)
+        acc_in = row if acc_in is None else acc_in + row
+    return np.where(inside[None], acc_in, acc_bd + zero).astype(np.float32)

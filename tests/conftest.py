@@ -27,6 +27,11 @@ def golden_small():
     return np.load(os.path.join(GOLDEN_DIR, "golden_small.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_cubic():
+    return np.load(os.path.join(GOLDEN_DIR, "golden_cubic.npz"))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def built_library():
     """The C-ABI library must exist for every test; build it here if nvcc is available."""

@@ -496,3 +496,47 @@ def test_c2e_full_size_properties(dev):
     c2e7 = cp360_b200.Cube2Equi(7)
     x7 = torch.randn(6, 1000, 7, 7, device=dev)
     assert torch.equal(c2e7.to_equi_max(x7), c2e7.to_equi_nn(x7).max(1)[0])
+
+
+# ------------------------------------------------------------------------------------------
+# Cube2Equi.to_equi_cv2 — bicubic variant. Bar: BIT-EXACT against the
+# reference's cv2.remap(INTER_CUBIC) output (tolerance 0, stricter than the 1e-5 asked).
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["w7", "w8", "w16"])
+def test_c2e_cubic_golden_bit_exact(dev, golden_cubic, tag):
+    w, seed = (int(v) for v in golden_cubic[tag + "_meta"])
+    cube = np.random.default_rng(seed).standard_normal((6, 1000, w, w)).astype(np.float32)
+    out = cp360_b200.Cube2Equi(w).to_equi_cv2(cube)          # numpy in -> numpy out (reference signature)
+    assert isinstance(out, np.ndarray) and out.shape == (1000, 2 * w, 4 * w) and out.dtype == np.float32
+    np.testing.assert_array_equal(out[golden_cubic["keep"]], golden_cubic[tag + "_planes"])
+    assert hashlib.sha256(out.tobytes()).digest() == golden_cubic[tag + "_sha256"].tobytes()
+
+
+@pytest.mark.parametrize("w,C,B", [(7, 1000, 2), (8, 12, 3), (3, 5, 1), (2, 4, 1), (16, 64, 2), (20, 4, 2),
+                                   (64, 3, 1), (8, 7, 1), (33, 2, 2)])
+def test_c2e_cubic_vs_oracle(dev, w, C, B):
+    rng = np.random.default_rng(w * 100 + C)
+    cube = rng.standard_normal((6 * B, C, w, w)).astype(np.float32)
+    face, coord = oc2e.build_maps(w)
+    out = cp360_b200.Cube2Equi(w).to_equi_cv2(torch.from_numpy(cube).to(dev))
+    assert out.is_cuda and tuple(out.shape) == (B, C, 2 * w, 4 * w)
+    out = out.cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(out[b], oc2e.to_equi_cv2(cube[6 * b:6 * b + 6], face, coord))
+
+
+def test_c2e_cubic_properties_full_size(dev):
+    """w = 256 (the e2c face size): linear in the input, a constant cube maps to that constant
+    wherever the 4x4 window lies inside the face (bicubic weights sum to 1 up to fp32 rounding)."""
+    w, C = 256, 2
+    c2e = cp360_b200.Cube2Equi(w)
+    g = torch.Generator(device=dev).manual_seed(3)
+    a = torch.randn((6, C, w, w), device=dev, generator=g)
+    ya, y2a = c2e.to_equi_cv2(a), c2e.to_equi_cv2(a * 2)
+    assert torch.equal(y2a, ya * 2)                              # exact: scaling by 2 commutes with rounding
+    ones = c2e.to_equi_cv2(torch.ones((6, 1, w, w), device=dev))[0, 0].cpu().numpy()
+    _, coord = oc2e.build_maps(w)
+    x0, y0, _, _ = oc2e.cubic_plan(coord)
+    inside = (x0 >= 0) & (x0 < w - 3) & (y0 >= 0) & (y0 < w - 3)
+    assert inside.mean() > 0.9
+    assert np.abs(ones[inside] - 1).max() <= 1e-6

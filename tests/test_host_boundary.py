@@ -128,3 +128,27 @@ def test_c2e_maps_bit_exact(golden_meta, golden_small):
             np.testing.assert_array_equal(((o.taps >> 14) & 0x3fff).astype(np.int32).reshape(2 * w, 4 * w) - 1, y0)
             np.testing.assert_array_equal((o.taps >> 28).reshape(2 * w, 4 * w), face.astype(np.uint32))
             assert o.M == M
+
+
+@pytest.mark.parametrize("w", [2, 7, 8, 16, 64, 256])
+def test_c2e_cubic_plan_bit_exact(w):
+    """cp360_c2e_build_cubic_plan == the oracle's cv2 fixed-point conversion of out_coord (row f4)."""
+    taps = np.empty(8 * w * w, dtype=np.uint32)
+    _lib.check(_lib.lib().cp360_c2e_build_cubic_plan(w, taps.ctypes.data))
+    face, coord = oc2e.build_maps(w)
+    x0, y0, fx, fy = oc2e.cubic_plan(coord)
+    t = taps.reshape(2 * w, 4 * w)
+    np.testing.assert_array_equal((t & 0x1ff).astype(np.int32) - 1, x0)
+    np.testing.assert_array_equal(((t >> 9) & 0x1ff).astype(np.int32) - 1, y0)
+    np.testing.assert_array_equal(((t >> 18) & 31).astype(np.int32), fx)
+    np.testing.assert_array_equal(((t >> 23) & 31).astype(np.int32), fy)
+    np.testing.assert_array_equal(t >> 28, face.astype(np.uint32))
+
+
+def test_c2e_cubic_errors():
+    lib = _lib.lib()
+    assert lib.cp360_c2e_build_cubic_plan(0, None) == 1
+    buf = np.empty(8, np.uint32)
+    assert lib.cp360_c2e_build_cubic_plan(513, buf.ctypes.data) == 4
+    assert lib.cp360_c2e_cubic_fwd(None, None, None, 1, 4, 8, None) == 1       # null pointers
+    assert lib.cp360_c2e_cubic_fwd(None, None, None, 0, 4, 8, None) == 0       # empty batch

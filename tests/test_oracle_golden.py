@@ -108,6 +108,36 @@ def test_c2e_maps_and_output(golden_meta, golden_small):
 
 
 # ---------------------------------------------------------------------------------------------
+# bicubic back-projection (row f4): fixture = the reference's own to_equi_cv2 output
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["w7", "w8", "w16"])
+def test_c2e_cubic_golden_bit_exact(golden_cubic, tag):
+    w, seed = (int(v) for v in golden_cubic[tag + "_meta"])
+    cube = np.random.default_rng(seed).standard_normal((6, 1000, w, w)).astype(np.float32)
+    face, coord = oc2e.build_maps(w)
+    out = oc2e.to_equi_cv2(cube, face, coord)
+    assert out.shape == (1000, 2 * w, 4 * w) and out.dtype == np.float32
+    np.testing.assert_array_equal(out[golden_cubic["keep"]], golden_cubic[tag + "_planes"])
+    assert hashlib.sha256(out.tobytes()).digest() == golden_cubic[tag + "_sha256"].tobytes()
+
+
+def test_c2e_cubic_table_against_cv2():
+    """Every 1/32-pixel fraction pair, interior and border windows, against cv2.remap itself."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    w = 9
+    src = rng.standard_normal((w, w, 4)).astype(np.float32)
+    # a synthetic out_coord sweeping x,y over [0, w-1] in 1/32 steps (plus off-grid values that round)
+    xs = np.arange(0, (w - 1) * 32 + 1, dtype=np.float64) / 32
+    gx, gy = np.meshgrid(xs, xs[::5] + 1e-3)
+    coord = np.stack([gx, np.minimum(gy, w - 1)], axis=-1)
+    want = cv2.remap(src, coord[..., 0].astype(np.float32), coord[..., 1].astype(np.float32), cv2.INTER_CUBIC)
+    cube = np.ascontiguousarray(np.broadcast_to(src.transpose(2, 0, 1)[None], (6, 4, w, w)))
+    got = oc2e.to_equi_cv2(cube, np.zeros(coord.shape[:2]), coord)
+    np.testing.assert_array_equal(got, want.transpose(2, 0, 1))
+
+
+# ---------------------------------------------------------------------------------------------
 # oracle.ref_port — the library-call port timed as bench.py's CPU baseline
 # ---------------------------------------------------------------------------------------------
 def test_ref_port_cubepad(golden_meta, golden_small):
