@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("CP360_LIB") or os.path.join(LIB_DIR, "libcp360.so")  
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 CU_SOURCES = ["common.cu", "cubepad.cu", "e2c.cu", "c2e.cu"]
-CPP_SOURCES = ["maps.cpp"]
+CPP_SOURCES = ["maps.cpp", "npy.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                      "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

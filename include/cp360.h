@@ -195,6 +195,27 @@ CP360_API int cp360_c2e_cubic_fwd(const float* cube_dev, const uint32_t* tap_dev
 CP360_API int cp360_c2e_bwd(const float* gequi_dev, const uint32_t* tap_dev, const float* wts_dev,
                   float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * .npy files either side of the path: cube score files `cube_feat/%06d.npy` [6,1000,7,7]
+ * (static_model/dataset_feat_extractor.py:187-189 writes, temporal_model/test_temporal.py:64,70 and
+ * data/dataset.py:65 read) and equirect result maps `%05d.npy` [14,28] (test_temporal.py:86-88).
+ * Host-only calls.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Parse the header of a .npy file (format 1.0 / 2.0 / 3.0). Any output may be NULL.
+ * descr: dtype string such as "<f4"; shape[max_dims]; data_offset: byte offset of the array data. */
+CP360_API int cp360_npy_read_header(const char* path, char* descr, int descr_len, int* ndim, int64_t* shape,
+                          int max_dims, int64_t* data_offset, int* fortran_order);
+
+/* Read a C-order little-endian f4 / f8 / f2 / u1 / i4 / i8 array into dst_host[n_elems] as float32
+ * (what torch.FloatTensor(np.load(path)) yields, test_temporal.py:70-78). n_elems must equal the
+ * file's element count (CP360_ERR_SHAPE otherwise). dst_host may be pinned memory. */
+CP360_API int cp360_npy_read_f32(const char* path, float* dst_host, int64_t n_elems);
+
+/* Write src_host as a float32 C-order .npy, byte-identical to numpy.save (format 1.0). Written to
+ * a temporary file and renamed, so readers never see a partial file. */
+CP360_API int cp360_npy_write_f32(const char* path, const float* src_host, int ndim, const int64_t* shape);
+
 #ifdef __cplusplus
 }
 #endif
