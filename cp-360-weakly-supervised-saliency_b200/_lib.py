@@ -29,6 +29,7 @@ SIGNATURES = {
     "cp360_e2c_build_map": (c_i32, [c_i32, c_i32, c_i32, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cp360_e2c_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp360_e2c_fwd_u8": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp, c_vp, c_vp]),
+    "cp360_e2c_cubepad_fwd": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_i64] + [c_i32] * 8 + [ctypes.c_float, c_vp, c_vp, c_vp]),
     "cp360_c2e_build_map": (c_i32, [c_i32, c_vp, c_vp]),
     "cp360_c2e_build_plan": (c_i32, [c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp360_c2e_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),

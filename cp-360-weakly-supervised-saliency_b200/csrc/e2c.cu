@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "cubepad_geom.h"
 
 namespace cp360 {
 
@@ -18,25 +19,60 @@ struct NormParams { float mean[4]; float std[4]; };
 
 constexpr int kE2cTileX = 32, kE2cTileY = 8;
 
+// Fused CubePad (e2c + im_norm + HWC->NCHW + CubePad(3) in one kernel — the input
+// of conv1, model/resnet_cubic.py:116-117). With WithPad the grid covers the PADDED faces; a thread
+// resolves its output pixel to the (face, pixel) CubePad copies it from (cubepad_geom.h, the table
+// the CubePad kernels use) and samples that pixel's map entry, so the halo is resampled from the
+// frame (+4.7 % gathers at 256/p3, all cache hits) instead of being copied from a faces tensor that
+// is never written. Values are bit-identical to CubePad(to_cube(frame)).
+struct NoPad { static constexpr bool kPad = false; };
+struct WithPad { static constexpr bool kPad = true; CubePadGeom g; };
+
+struct E2cPix { int f, map_idx, out_pix, out_plane; };
+
+template <class GEOM>
+__device__ __forceinline__ bool e2c_locate(const GEOM& geom, int w, E2cPix* q) {
+  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
+  if constexpr (GEOM::kPad) {
+    const int Ho = geom.g.Ho, Wo = geom.g.Wo;
+    const int tiles_y = (Ho + kE2cTileY - 1) / kE2cTileY;
+    q->f = blockIdx.y / tiles_y;
+    const int oy = (blockIdx.y - q->f * tiles_y) * kE2cTileY + threadIdx.y;
+    if (ox >= Wo || oy >= Ho) return false;
+    int sf;
+    const int sp = cubepad_src(geom.g, q->f, oy, ox, &sf);
+    q->map_idx = sf * w * w + sp;
+    q->out_pix = oy * Wo + ox;
+    q->out_plane = Ho * Wo;
+  } else {
+    const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
+    q->f = blockIdx.y / tiles_y;
+    const int oy = (blockIdx.y - q->f * tiles_y) * kE2cTileY + threadIdx.y;
+    if (ox >= w || oy >= w) return false;
+    q->map_idx = q->f * w * w + oy * w + ox;
+    q->out_pix = oy * w + ox;
+    q->out_plane = w * w;
+  }
+  return true;
+}
+
 template <int C>
 __device__ __forceinline__ void load_px(const float* __restrict__ p, float (&v)[C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) v[c] = __ldg(p + c);
 }
 
-template <int C, int LAYOUT, bool NORM>
+template <int C, int LAYOUT, bool NORM, class GEOM>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
-           float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm) {
+           float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm,
+           const __grid_constant__ GEOM geom) {
   pdl_trigger();
   pdl_wait();
-  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  const int f = blockIdx.y / tiles_y;
-  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
-  if (ox >= w || oy >= w) return;
-  const int ww = w * w;
-  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  E2cPix q;
+  if (!e2c_locate(geom, w, &q)) return;
+  const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
+  const uint32_t p = __ldg(packed + q.map_idx);
   const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
   const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
@@ -61,9 +97,9 @@ e2c_kernel(const float* __restrict__ frames, const uint32_t* __restrict__ packed
       v = __fadd_rn(v, __fmul_rn(a11, w11));
       if (NORM) v = __fdiv_rn(__fsub_rn(v, nrm.mean[c]), nrm.std[c]);   // utils/utils.py:28-33
       if (LAYOUT == CP360_LAYOUT_NCHW)
-        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox, v);
+        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + pix, v);
       else
-        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+        faces[((b * 6 + f) * (int64_t)ww + pix) * C + c] = v;
     }
   }
 }
@@ -88,22 +124,20 @@ __device__ __forceinline__ void realign6(const float4& a, const float4& b, float
   for (int k = 0; k < 6; ++k) v[k] = s1 ? t[k + 1] : t[k];
 }
 
-template <int LAYOUT, bool NORM>
+template <int LAYOUT, bool NORM, class GEOM>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
-               float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm) {
+               float* __restrict__ faces, int64_t B, int Hin, int Win, int w, NormParams nrm,
+               const __grid_constant__ GEOM geom) {
   constexpr int C = 3;
   CP360_TRACE_BEGIN(3)
   pdl_trigger();
   pdl_wait();
   CP360_TRACE_T0(1);
-  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  const int f = blockIdx.y / tiles_y;
-  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
-  if (ox >= w || oy >= w) return;
-  const int ww = w * w;
-  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  E2cPix q;
+  if (!e2c_locate(geom, w, &q)) return;
+  const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
+  const uint32_t p = __ldg(packed + q.map_idx);
   const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
   const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
@@ -118,7 +152,6 @@ e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ pa
   const int need = o == 3 ? 12 : 8;                        // floats fetched per window
   // only the last frame can run off the end of the buffer (elsewhere the overrun lands in the next frame)
   const bool risky = (y1_ok ? a0 + row_floats : a0) + need > frame_floats;
-  const int pix = oy * w + ox;
 
   for (int64_t b_begin = (int64_t)blockIdx.z * kE2cFramesPerThread; b_begin < B;
        b_begin += (int64_t)gridDim.z * kE2cFramesPerThread) {
@@ -173,19 +206,17 @@ e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ pa
 }
 
 // any channel count (no normalisation)
-template <int LAYOUT>
+template <int LAYOUT, class GEOM>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel_anyc(const float* __restrict__ frames, const uint32_t* __restrict__ packed,
-                float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w) {
+                float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w,
+                const __grid_constant__ GEOM geom) {
   pdl_trigger();
   pdl_wait();
-  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  const int f = blockIdx.y / tiles_y;
-  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
-  if (ox >= w || oy >= w) return;
-  const int ww = w * w;
-  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  E2cPix q;
+  if (!e2c_locate(geom, w, &q)) return;
+  const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
+  const uint32_t p = __ldg(packed + q.map_idx);
   const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
   const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
@@ -204,9 +235,9 @@ e2c_kernel_anyc(const float* __restrict__ frames, const uint32_t* __restrict__ p
       v = __fadd_rn(v, __fmul_rn(a10, w10));
       v = __fadd_rn(v, __fmul_rn(a11, w11));
       if (LAYOUT == CP360_LAYOUT_NCHW)
-        faces[((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox] = v;
+        faces[((b * 6 + f) * C + c) * (int64_t)ww + pix] = v;
       else
-        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+        faces[((b * 6 + f) * (int64_t)ww + pix) * C + c] = v;
     }
   }
 }
@@ -217,11 +248,11 @@ e2c_kernel_anyc(const float* __restrict__ frames, const uint32_t* __restrict__ p
 // bilinear arithmetic. The 256 quotients live in shared memory; a tap pair of a C = 3 row is six
 // contiguous bytes, fetched as three aligned words and realigned with funnel shifts. H2D traffic
 // and DRAM reads are a quarter of the fp32 path.
-template <int LAYOUT, bool NORM>
+template <int LAYOUT, bool NORM, class GEOM>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel_u8c3(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ packed,
                 float* __restrict__ faces, int64_t B, int Hin, int Win, int w, float denom,
-                NormParams nrm) {
+                NormParams nrm, const __grid_constant__ GEOM geom) {
   constexpr int C = 3;
   __shared__ float lut[256];
   const int tid = threadIdx.y * kE2cTileX + threadIdx.x;
@@ -229,13 +260,10 @@ e2c_kernel_u8c3(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
   lut[tid] = __fdiv_rn((float)tid, denom);                 // block is 256 threads
   __syncthreads();
   pdl_wait();
-  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  const int f = blockIdx.y / tiles_y;
-  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
-  if (ox >= w || oy >= w) return;
-  const int ww = w * w;
-  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  E2cPix q;
+  if (!e2c_locate(geom, w, &q)) return;
+  const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
+  const uint32_t p = __ldg(packed + q.map_idx);
   const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
   const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
@@ -277,31 +305,29 @@ e2c_kernel_u8c3(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
       v = __fadd_rn(v, __fmul_rn(a11, w11));
       if (NORM) v = __fdiv_rn(__fsub_rn(v, nrm.mean[c]), nrm.std[c]);
       if (LAYOUT == CP360_LAYOUT_NCHW)
-        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox, v);
+        __stcs(faces + ((b * 6 + f) * C + c) * (int64_t)ww + pix, v);
       else
-        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+        faces[((b * 6 + f) * (int64_t)ww + pix) * C + c] = v;
     }
   }
 }
 
 // uint8, any channel count / alignment (byte loads)
-template <int LAYOUT>
+template <int LAYOUT, class GEOM>
 __global__ void __launch_bounds__(kE2cTileX * kE2cTileY)
 e2c_kernel_u8_anyc(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ packed,
-                   float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w, float denom) {
+                   float* __restrict__ faces, int64_t B, int Hin, int Win, int C, int w, float denom,
+                   const __grid_constant__ GEOM geom) {
   __shared__ float lut[256];
   const int tid = threadIdx.y * kE2cTileX + threadIdx.x;
   pdl_trigger();
   lut[tid] = __fdiv_rn((float)tid, denom);
   __syncthreads();
   pdl_wait();
-  const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  const int f = blockIdx.y / tiles_y;
-  const int oy = (blockIdx.y - f * tiles_y) * kE2cTileY + threadIdx.y;
-  if (ox >= w || oy >= w) return;
-  const int ww = w * w;
-  const uint32_t p = __ldg(packed + (size_t)f * ww + oy * w + ox);
+  E2cPix q;
+  if (!e2c_locate(geom, w, &q)) return;
+  const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
+  const uint32_t p = __ldg(packed + q.map_idx);
   const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
   const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
@@ -320,21 +346,123 @@ e2c_kernel_u8_anyc(const uint8_t* __restrict__ frames, const uint32_t* __restric
       v = __fadd_rn(v, __fmul_rn(a10, w10));
       v = __fadd_rn(v, __fmul_rn(a11, w11));
       if (LAYOUT == CP360_LAYOUT_NCHW)
-        faces[((b * 6 + f) * C + c) * (int64_t)ww + oy * w + ox] = v;
+        faces[((b * 6 + f) * C + c) * (int64_t)ww + pix] = v;
       else
-        faces[((b * 6 + f) * (int64_t)ww + oy * w + ox) * C + c] = v;
+        faces[((b * 6 + f) * (int64_t)ww + pix) * C + c] = v;
     }
   }
 }
 
-template <int C, int LAYOUT>
-static void launch_c(bool norm, dim3 grid, dim3 block, cudaStream_t st, const float* frames,
-                     const uint32_t* packed, float* faces, int64_t B, int Hin, int Win, int w,
-                     const NormParams& nrm) {
-  if (norm)
-    launch_kernel(e2c_kernel<C, LAYOUT, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
+// ---- dispatch -----------------------------------------------------------------------------------
+struct E2cArgs {
+  const void* frames;
+  bool u8;
+  const uint32_t* packed;
+  float* out;
+  int64_t B;
+  int Hin, Win, C, w, layout;
+  float denom;
+  bool norm;
+  NormParams nrm;
+  cudaStream_t st;
+};
+
+template <class GEOM>
+static int e2c_dispatch(const E2cArgs& a, const GEOM& geom, int out_h, int out_w) {
+  const int tiles_y = (out_h + kE2cTileY - 1) / kE2cTileY;
+  dim3 block(kE2cTileX, kE2cTileY);
+  dim3 grid((out_w + kE2cTileX - 1) / kE2cTileX, 6 * tiles_y, (unsigned)std::min<int64_t>(a.B, 65535));
+  const bool nchw = a.layout == CP360_LAYOUT_NCHW;
+  const int64_t B = a.B;
+  const int Hin = a.Hin, Win = a.Win, C = a.C, w = a.w;
+  cudaStream_t st = a.st;
+#define CP360_E2C_LN(KERN, ...)                                                                               \
+  do {                                                                                                        \
+    if (nchw) {                                                                                               \
+      if (a.norm) launch_kernel(KERN<CP360_LAYOUT_NCHW, true, GEOM>, grid, block, 0, st, __VA_ARGS__, geom);  \
+      else launch_kernel(KERN<CP360_LAYOUT_NCHW, false, GEOM>, grid, block, 0, st, __VA_ARGS__, geom);        \
+    } else {                                                                                                  \
+      if (a.norm) launch_kernel(KERN<CP360_LAYOUT_NHWC, true, GEOM>, grid, block, 0, st, __VA_ARGS__, geom);  \
+      else launch_kernel(KERN<CP360_LAYOUT_NHWC, false, GEOM>, grid, block, 0, st, __VA_ARGS__, geom);        \
+    }                                                                                                         \
+  } while (0)
+#define CP360_E2C_L(KERN, ...)                                                                        \
+  do {                                                                                                \
+    if (nchw) launch_kernel(KERN<CP360_LAYOUT_NCHW, GEOM>, grid, block, 0, st, __VA_ARGS__, geom);    \
+    else launch_kernel(KERN<CP360_LAYOUT_NHWC, GEOM>, grid, block, 0, st, __VA_ARGS__, geom);         \
+  } while (0)
+  if (a.u8) {
+    const uint8_t* frames = static_cast<const uint8_t*>(a.frames);
+    if (C == 3 && ((uintptr_t)frames % 4) == 0) {
+      CP360_E2C_LN(e2c_kernel_u8c3, frames, a.packed, a.out, B, Hin, Win, w, a.denom, a.nrm);
+    } else {
+      CP360_CHECK_ARG(!a.norm, CP360_ERR_ALIGN, "fused normalisation needs 4 B-aligned uint8 frames");
+      CP360_E2C_L(e2c_kernel_u8_anyc, frames, a.packed, a.out, B, Hin, Win, C, w, a.denom);
+    }
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
+  const float* frames = static_cast<const float*>(a.frames);
+  const bool vec_ok = C == 3 && ((uintptr_t)frames % 16) == 0 && ((int64_t)Win * C * 4) % 16 == 0 &&
+                      ((int64_t)Hin * Win * C * 4) % 16 == 0;
+  if (vec_ok) {
+    grid.z = (unsigned)std::min<int64_t>((B + kE2cFramesPerThread - 1) / kE2cFramesPerThread, 65535);
+    CP360_E2C_LN(e2c_kernel_c3v, frames, a.packed, a.out, B, Hin, Win, w, a.nrm);
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
+#define CP360_E2C_CASE(CC)                                                                                     \
+  case CC:                                                                                                     \
+    if (nchw) {                                                                                                \
+      if (a.norm) launch_kernel(e2c_kernel<CC, CP360_LAYOUT_NCHW, true, GEOM>, grid, block, 0, st, frames, a.packed, a.out, B, Hin, Win, w, a.nrm, geom);  \
+      else launch_kernel(e2c_kernel<CC, CP360_LAYOUT_NCHW, false, GEOM>, grid, block, 0, st, frames, a.packed, a.out, B, Hin, Win, w, a.nrm, geom);        \
+    } else {                                                                                                   \
+      if (a.norm) launch_kernel(e2c_kernel<CC, CP360_LAYOUT_NHWC, true, GEOM>, grid, block, 0, st, frames, a.packed, a.out, B, Hin, Win, w, a.nrm, geom);  \
+      else launch_kernel(e2c_kernel<CC, CP360_LAYOUT_NHWC, false, GEOM>, grid, block, 0, st, frames, a.packed, a.out, B, Hin, Win, w, a.nrm, geom);        \
+    }                                                                                                          \
+    break;
+  switch (C) {
+    CP360_E2C_CASE(1)
+    CP360_E2C_CASE(3)
+    CP360_E2C_CASE(4)
+    default:
+      CP360_E2C_L(e2c_kernel_anyc, frames, a.packed, a.out, B, Hin, Win, C, w);
+  }
+#undef CP360_E2C_CASE
+#undef CP360_E2C_L
+#undef CP360_E2C_LN
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+// validation shared by the three entry points; *run = false when there is nothing to launch
+static int e2c_prepare(E2cArgs* a, const float* mean_host, const float* std_host, bool* run) {
+  *run = false;
+  CP360_CHECK_ARG(a->B >= 0 && a->C >= 0 && a->w > 0 && a->Hin > 0 && a->Win > 0, CP360_ERR_BAD_ARG, "bad size");
+  CP360_CHECK_ARG(a->Hin * 2 == a->Win, CP360_ERR_SHAPE,
+                  "input must be 2:1 equirectangular (got %dx%d)", a->Win, a->Hin);
+  CP360_CHECK_ARG(a->Win <= 2047 && a->Hin <= 1023, CP360_ERR_RANGE, "packed map supports up to 2047x1023");
+  CP360_CHECK_ARG(a->layout == CP360_LAYOUT_NCHW || a->layout == CP360_LAYOUT_NHWC,
+                  CP360_ERR_BAD_ARG, "unknown layout %d", a->layout);
+  CP360_CHECK_ARG(!a->u8 || a->denom > 0.0f, CP360_ERR_BAD_ARG, "denom must be positive");
+  a->norm = mean_host != nullptr || std_host != nullptr;
+  if (a->u8)
+    CP360_CHECK_ARG(!a->norm || (mean_host && std_host && a->C == 3), CP360_ERR_BAD_ARG,
+                    "fused normalisation of uint8 frames needs mean and std and C == 3");
   else
-    launch_kernel(e2c_kernel<C, LAYOUT, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
+    CP360_CHECK_ARG(!a->norm || (mean_host && std_host && a->C <= 4 && a->C != 2), CP360_ERR_BAD_ARG,
+                    "fused normalisation needs mean and std and C in {1,3,4}");
+  if (a->B == 0 || a->C == 0) return CP360_OK;
+  CP360_CHECK_ARG(a->frames && a->packed && a->out, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG((a->u8 || ((uintptr_t)a->frames % 4) == 0) && ((uintptr_t)a->out % 4) == 0 &&
+                      ((uintptr_t)a->packed % 4) == 0, CP360_ERR_ALIGN, "pointer not 4 B aligned");
+  int rc = require_device();
+  if (rc != CP360_OK) return rc;
+  a->nrm = NormParams{};
+  if (a->norm)
+    for (int c = 0; c < a->C; ++c) { a->nrm.mean[c] = mean_host[c]; a->nrm.std[c] = std_host[c]; }
+  *run = true;
+  return CP360_OK;
 }
 
 }  // namespace cp360
@@ -344,107 +472,36 @@ using namespace cp360;
 extern "C" int cp360_e2c_fwd(const float* frames, const uint32_t* packed, float* faces, int64_t B,
                              int Hin, int Win, int C, int w, int out_layout,
                              const float* mean_host, const float* std_host, void* stream) {
-  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0 && Hin > 0 && Win > 0, CP360_ERR_BAD_ARG, "bad size");
-  CP360_CHECK_ARG(Hin * 2 == Win, CP360_ERR_SHAPE,
-                  "input must be 2:1 equirectangular (got %dx%d)", Win, Hin);
-  CP360_CHECK_ARG(Win <= 2047 && Hin <= 1023, CP360_ERR_RANGE, "packed map supports up to 2047x1023");
-  CP360_CHECK_ARG(out_layout == CP360_LAYOUT_NCHW || out_layout == CP360_LAYOUT_NHWC,
-                  CP360_ERR_BAD_ARG, "unknown layout %d", out_layout);
-  const bool norm = mean_host != nullptr || std_host != nullptr;
-  CP360_CHECK_ARG(!norm || (mean_host && std_host && C <= 4 && C != 2), CP360_ERR_BAD_ARG,
-                  "fused normalisation needs mean and std and C in {1,3,4}");
-  if (B == 0 || C == 0) return CP360_OK;
-  CP360_CHECK_ARG(frames && packed && faces, CP360_ERR_BAD_ARG, "null pointer");
-  CP360_CHECK_ARG(((uintptr_t)frames % 4) == 0 && ((uintptr_t)faces % 4) == 0 &&
-                      ((uintptr_t)packed % 4) == 0, CP360_ERR_ALIGN, "pointer not 4 B aligned");
-  int rc = require_device();
-  if (rc != CP360_OK) return rc;
-  NormParams nrm = {};
-  if (norm)
-    for (int c = 0; c < C; ++c) { nrm.mean[c] = mean_host[c]; nrm.std[c] = std_host[c]; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  dim3 block(kE2cTileX, kE2cTileY);
-  dim3 grid((w + kE2cTileX - 1) / kE2cTileX, 6 * tiles_y, (unsigned)std::min<int64_t>(B, 65535));
-  const bool nchw = out_layout == CP360_LAYOUT_NCHW;
-#define CP360_E2C_CASE(CC)                                                                      \
-  case CC:                                                                                      \
-    if (nchw) launch_c<CC, CP360_LAYOUT_NCHW>(norm, grid, block, st, frames, packed, faces, B,  \
-                                               Hin, Win, w, nrm);                               \
-    else launch_c<CC, CP360_LAYOUT_NHWC>(norm, grid, block, st, frames, packed, faces, B, Hin,  \
-                                          Win, w, nrm);                                         \
-    break;
-  const bool vec_ok = C == 3 && ((uintptr_t)frames % 16) == 0 && ((int64_t)Win * C * 4) % 16 == 0 &&
-                      ((int64_t)Hin * Win * C * 4) % 16 == 0;
-  if (vec_ok) {
-    grid.z = (unsigned)std::min<int64_t>((B + kE2cFramesPerThread - 1) / kE2cFramesPerThread, 65535);
-    if (nchw) {
-      if (norm) launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NCHW, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
-      else launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NCHW, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
-    } else {
-      if (norm) launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NHWC, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
-      else launch_kernel(e2c_kernel_c3v<CP360_LAYOUT_NHWC, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, nrm);
-    }
-    CP360_LAUNCHED();
-    return CP360_OK;
-  }
-  switch (C) {
-    CP360_E2C_CASE(1)
-    CP360_E2C_CASE(3)
-    CP360_E2C_CASE(4)
-    default:
-      if (nchw)
-        launch_kernel(e2c_kernel_anyc<CP360_LAYOUT_NCHW>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w);
-      else
-        launch_kernel(e2c_kernel_anyc<CP360_LAYOUT_NHWC>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w);
-  }
-#undef CP360_E2C_CASE
-  CP360_LAUNCHED();
-  return CP360_OK;
+  E2cArgs a = {frames, false, packed, faces, B, Hin, Win, C, w, out_layout, 1.0f, false, {}, (cudaStream_t)stream};
+  bool run;
+  int rc = e2c_prepare(&a, mean_host, std_host, &run);
+  if (rc != CP360_OK || !run) return rc;
+  return e2c_dispatch(a, NoPad{}, w, w);
 }
 
 extern "C" int cp360_e2c_fwd_u8(const uint8_t* frames, const uint32_t* packed, float* faces, int64_t B,
                                 int Hin, int Win, int C, int w, int out_layout, float denom,
                                 const float* mean_host, const float* std_host, void* stream) {
-  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0 && Hin > 0 && Win > 0, CP360_ERR_BAD_ARG, "bad size");
-  CP360_CHECK_ARG(Hin * 2 == Win, CP360_ERR_SHAPE,
-                  "input must be 2:1 equirectangular (got %dx%d)", Win, Hin);
-  CP360_CHECK_ARG(Win <= 2047 && Hin <= 1023, CP360_ERR_RANGE, "packed map supports up to 2047x1023");
-  CP360_CHECK_ARG(out_layout == CP360_LAYOUT_NCHW || out_layout == CP360_LAYOUT_NHWC,
-                  CP360_ERR_BAD_ARG, "unknown layout %d", out_layout);
-  CP360_CHECK_ARG(denom > 0.0f, CP360_ERR_BAD_ARG, "denom must be positive");
-  const bool norm = mean_host != nullptr || std_host != nullptr;
-  CP360_CHECK_ARG(!norm || (mean_host && std_host && C == 3), CP360_ERR_BAD_ARG,
-                  "fused normalisation of uint8 frames needs mean and std and C == 3");
-  if (B == 0 || C == 0) return CP360_OK;
-  CP360_CHECK_ARG(frames && packed && faces, CP360_ERR_BAD_ARG, "null pointer");
-  CP360_CHECK_ARG(((uintptr_t)faces % 4) == 0 && ((uintptr_t)packed % 4) == 0, CP360_ERR_ALIGN,
-                  "pointer not 4 B aligned");
-  int rc = require_device();
-  if (rc != CP360_OK) return rc;
-  NormParams nrm = {};
-  if (norm)
-    for (int c = 0; c < C; ++c) { nrm.mean[c] = mean_host[c]; nrm.std[c] = std_host[c]; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_y = (w + kE2cTileY - 1) / kE2cTileY;
-  dim3 block(kE2cTileX, kE2cTileY);
-  dim3 grid((w + kE2cTileX - 1) / kE2cTileX, 6 * tiles_y, (unsigned)std::min<int64_t>(B, 65535));
-  const bool nchw = out_layout == CP360_LAYOUT_NCHW;
-  if (C == 3 && ((uintptr_t)frames % 4) == 0) {
-    if (nchw) {
-      if (norm) launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NCHW, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
-      else launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NCHW, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
-    } else {
-      if (norm) launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NHWC, true>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
-      else launch_kernel(e2c_kernel_u8c3<CP360_LAYOUT_NHWC, false>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, w, denom, nrm);
-    }
-  } else {
-    CP360_CHECK_ARG(!norm, CP360_ERR_ALIGN, "fused normalisation needs 4 B-aligned uint8 frames");
-    if (nchw) launch_kernel(e2c_kernel_u8_anyc<CP360_LAYOUT_NCHW>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w, denom);
-    else launch_kernel(e2c_kernel_u8_anyc<CP360_LAYOUT_NHWC>, grid, block, 0, st, frames, packed, faces, B, Hin, Win, C, w, denom);
-  }
-  CP360_LAUNCHED();
-  return CP360_OK;
+  E2cArgs a = {frames, true, packed, faces, B, Hin, Win, C, w, out_layout, denom, false, {}, (cudaStream_t)stream};
+  bool run;
+  int rc = e2c_prepare(&a, mean_host, std_host, &run);
+  if (rc != CP360_OK || !run) return rc;
+  return e2c_dispatch(a, NoPad{}, w, w);
+}
+
+extern "C" int cp360_e2c_cubepad_fwd(const void* frames, int frames_u8, const uint32_t* packed, float* padded,
+                                     int64_t B, int Hin, int Win, int C, int w, int pl, int pr, int pt,
+                                     int pd, float denom, const float* mean_host, const float* std_host,
+                                     void* stream) {
+  E2cArgs a = {frames, frames_u8 != 0, packed, padded, B, Hin, Win, C, w, CP360_LAYOUT_NCHW,
+               frames_u8 ? denom : 1.0f, false, {}, (cudaStream_t)stream};
+  WithPad geom;
+  CP360_CHECK_ARG(w > 0 && make_geom(w, w, pl, pr, pt, pd, &geom.g), CP360_ERR_SHAPE,
+                  "CubePad needs 0 <= pad <= face width (w=%d, pads l%d r%d t%d d%d)", w, pl, pr, pt, pd);
+  bool run;
+  int rc = e2c_prepare(&a, mean_host, std_host, &run);
+  if (rc != CP360_OK || !run) return rc;
+  return e2c_dispatch(a, geom, geom.g.Ho, geom.g.Wo);
 }
 
 #ifdef CP360_TRACE

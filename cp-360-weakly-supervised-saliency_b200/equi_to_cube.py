@@ -3,6 +3,7 @@
     e2c = Equi2Cube(output_width, in_image, vfov=90)      # builds the sampling maps (host, once)
     faces = e2c.to_cube(in_image)                         # dict {0..5: ndarray[w,w,C]}  (reference API)
     t = e2c.to_cube_tensor(frames)                        # [B,H,W,C] cuda -> [6B,C,w,w]  (addition)
+    x = e2c.to_padded_cube_tensor(frames, 3, mean, std)   # ... -> CubePad(3)(im_norm(faces)), one kernel
 
 Map construction is cp360_e2c_build_map (C++, float64, same operation order as the numpy
 code); resampling is cp360_e2c_fwd on the GPU with cv2.remap's fixed-point arithmetic.
@@ -97,6 +98,45 @@ class Equi2Cube:
             else:
                 _lib.check(_lib.lib().cp360_e2c_fwd(
                     frames.data_ptr(), pm.data_ptr(), out.data_ptr(), b, h, wi, c, w, lay, mp, sp, st))
+        return out
+
+    def to_padded_cube_tensor(self, frames, lrtd_pad, mean=None, std=None, out=None, denom=255.0):
+        """frames [B,H,W,C] cuda (float32 or uint8) -> CubePad(lrtd_pad)(faces) [6B,C,w+pt+pd,w+pl+pr]
+        in one kernel (cp360_e2c_cubepad_fwd): to_cube + im_norm + NHWC->NCHW + the CubePad(3) in front
+        of conv1 (dataset_feat_extractor.py:145-157, resnet_cubic.py:116-117) without writing the
+        unpadded faces. Bit-identical to CubePad(lrtd_pad)(to_cube_tensor(frames, mean=..., std=...))."""
+        from .cube_pad import get_pad_size
+        if not isinstance(frames, torch.Tensor) or not frames.is_cuda:
+            raise RuntimeError("to_padded_cube_tensor expects a CUDA tensor (no CPU fallback)")
+        if frames.dim() == 3:
+            frames = frames.unsqueeze(0)
+        is_u8 = frames.dtype == torch.uint8
+        if not is_u8 and frames.dtype != torch.float32:
+            frames = frames.float()
+        frames = frames.contiguous()
+        b, h, wi, c = frames.shape
+        if (h, wi) != (self.input_height, self.input_width):
+            raise ValueError("frame is %dx%d, maps were built for %dx%d" % (wi, h, self.input_width, self.input_height))
+        pl, pr, pt, pd = get_pad_size(lrtd_pad)
+        w = self.output_width
+        shape = (6 * b, c, w + pt + pd, w + pl + pr)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=frames.device)
+        elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("out must be a contiguous float32 tensor of shape %s" % (shape,))
+        mp = sp = None
+        if mean is not None or std is not None:
+            m_arr = np.ascontiguousarray(mean, dtype=np.float32)
+            s_arr = np.ascontiguousarray(std, dtype=np.float32)
+            if m_arr.size != c or s_arr.size != c:
+                raise ValueError("mean/std need %d entries" % c)
+            mp, sp = m_arr.ctypes.data, s_arr.ctypes.data
+        pm = self._map_on(frames.device)
+        with torch.cuda.device(frames.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().cp360_e2c_cubepad_fwd(
+                frames.data_ptr(), int(is_u8), pm.data_ptr(), out.data_ptr(), b, h, wi, c, w, pl, pr, pt, pd,
+                float(denom), mp, sp, st))
         return out
 
     # ------------------------------------------------------------------ reference API

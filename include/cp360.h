@@ -150,6 +150,19 @@ CP360_API int cp360_e2c_fwd_u8(const uint8_t* frames_dev, const uint32_t* packed
                      int64_t B, int Hin, int Win, int C, int w, int out_layout, float denom,
                      const float* mean_host, const float* std_host, void* stream);
 
+/* Device: padded[6B,C,w+pt+pd,w+pl+pr] = CubePad(im_norm(to_cube(frame))) in ONE kernel — the chain
+ * dataset_feat_extractor.py:145-157 (to_cube, im_norm, stack, NHWC->NCHW) + CubePad(3) in front of conv1
+ * (model/resnet_cubic.py:116-117): the faces tensor is never materialised, every padded pixel is
+ * resampled through the map entry of the face pixel CubePad would have copied (same geometry table
+ * as cp360_cubepad_fwd), so the result is bit-identical to cp360_e2c_fwd followed by cp360_cubepad_fwd.
+ * frames_u8 != 0: frames_dev is uint8 [B,Hin,Win,C] converted as float32(u8)/denom (see cp360_e2c_fwd_u8),
+ * else float [B,Hin,Win,C] and denom is ignored. mean/std as in cp360_e2c_fwd. Output is NCHW.
+ * Pad order l, r, t, d (cube_pad.py:12-20); CP360_ERR_SHAPE if a pad exceeds w. */
+CP360_API int cp360_e2c_cubepad_fwd(const void* frames_dev, int frames_u8, const uint32_t* packed_dev,
+                          float* padded_dev, int64_t B, int Hin, int Win, int C, int w, int pl, int pr,
+                          int pt, int pd, float denom, const float* mean_host, const float* std_host,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Cube2Equi — utils/cube_to_equi.py:11-66
  * ---------------------------------------------------------------------------------------- */

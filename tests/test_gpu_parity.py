@@ -393,6 +393,54 @@ def test_e2c_full_size_properties(dev):
 
 
 # ------------------------------------------------------------------------------------------
+# Equi2Cube + im_norm + CubePad in one kernel. Bar: bit-exact against the
+# oracle chain (to_cube -> normalise -> cubepad) and against the two separate kernels.
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,H,W,C,B,pad", [(24, 96, 192, 3, 3, 3), (20, 50, 100, 3, 2, 1), (16, 64, 128, 1, 2, 2),
+                                           (16, 64, 128, 4, 1, [1, 2, 3, 0]), (12, 48, 96, 7, 2, 3),
+                                           (8, 32, 64, 3, 5, [0, 0, 0, 0]), (9, 32, 64, 3, 1, 9)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_e2c_cubepad_fused_vs_oracle(dev, w, H, W, C, B, pad, u8):
+    rng = np.random.default_rng(w * 10 + C)
+    if u8:
+        raw = rng.integers(0, 256, size=(B, H, W, C), dtype=np.uint8)
+        frames = (raw / 255.0).astype(np.float32)                         # the reference's conversion
+    else:
+        raw = frames = rng.random((B, H, W, C), dtype=np.float32)
+    e2c = cp360_b200.Equi2Cube(w, frames[0])
+    sx, sy = oe2c.fixed_maps(w, H, W)
+    got = e2c.to_padded_cube_tensor(torch.from_numpy(raw).to(dev), pad)
+    faces = np.concatenate([oe2c.to_cube(frames[b], sx, sy) for b in range(B)])      # [6B,w,w,C]
+    want = ocp.cubepad(np.ascontiguousarray(faces.transpose(0, 3, 1, 2)), pad)
+    assert tuple(got.shape) == want.shape
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # == the two separate kernels
+    two = cp360_b200.CubePad(pad)(e2c.to_cube_tensor(torch.from_numpy(raw).to(dev)))
+    assert torch.equal(got, two)
+
+
+def test_e2c_cubepad_fused_norm_and_full_size(dev):
+    """The conv1 input of the static model: 1920x960 uint8 frames -> normalised, CubePad(3)-padded
+    [6B,3,262,262], identical to e2c(+im_norm) followed by CubePad(3)."""
+    H, W, w = 960, 1920, 256
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    e2c = cp360_b200.Equi2Cube(w, np.empty((H, W, 3), np.float32))
+    g = torch.Generator(device=dev).manual_seed(11)
+    u8 = torch.randint(0, 256, (5, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
+    got = e2c.to_padded_cube_tensor(u8, 3, mean=mean, std=std)
+    want = cp360_b200.CubePad(3)(e2c.to_cube_tensor(u8, mean=mean, std=std))
+    assert tuple(got.shape) == (30, 3, 262, 262) and torch.equal(got, want)
+    f32 = torch.rand((3, H, W, 3), device=dev, generator=g)
+    assert torch.equal(e2c.to_padded_cube_tensor(f32, 3), cp360_b200.CubePad(3)(e2c.to_cube_tensor(f32)))
+    out = torch.empty((18, 3, 262, 262), device=dev)
+    assert e2c.to_padded_cube_tensor(f32, 3, out=out) is out
+    with pytest.raises(_lib.CP360Error):
+        e2c.to_padded_cube_tensor(f32, 257)                                # pad > face width
+    with pytest.raises(ValueError):
+        e2c.to_padded_cube_tensor(f32, 3, out=torch.empty((18, 3, 256, 256), device=dev))
+
+
+# ------------------------------------------------------------------------------------------
 # Cube2Equi
 # ------------------------------------------------------------------------------------------
 def test_c2e_golden(dev, golden_meta, golden_small):
