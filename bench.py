@@ -296,6 +296,26 @@ def run_b200(args, rank, world, local_rank):
         ms = float(t.item())
     value = world * B * K / (ms / 1e3)
 
+    # ---- variant (row f2 of SURVEY §8): e2c and the CubePad(3) in front of conv1 as one kernel; same
+    # outputs from site 0 on, the unpadded faces are never written. Reported beside the headline.
+    fused_first = None
+    if world == 1 and not args.no_graph:
+        pipe.fuse_first_site = True
+        g2 = pipe.capture(frames)
+        for _ in range(W):
+            g2.replay()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(K):
+            g2.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms2 = ev0.elapsed_time(ev1)
+        fused_first = {"value": round(B * K / (ms2 / 1e3), 1), "unit": "frames/s", "ms_per_step": round(ms2 / K, 4),
+                       "what": "same chain with cp360_e2c_cubepad_fwd replacing e2c + CubePad(3) (21 launches per step)"}
+        pipe.fuse_first_site = False
+        del g2
+
     # ---- per-launch CUDA events on the launching stream: which kernel dominates, and its GB/s
     names, marks = [], []
 
@@ -380,15 +400,22 @@ def run_b200(args, rank, world, local_rank):
         E = max(4, min(K, 40))
         out_host = torch.empty((E, B, 2 * fw, 4 * fw), dtype=torch.float32).pin_memory()
 
+        wall = []
+
         def run_e2e(host):
             batches = [host[i % len(host)] for i in range(E)]
             pipe.process_host(batches[:4], out_host[:4])          # warm-up (staging buffers, streams)
             torch.cuda.synchronize()
             barrier()
-            t0 = time.perf_counter()
-            pipe.process_host(batches, out_host)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()                      # the copy stream waits for the compute stream first, so e0 precedes every H2D
+            pipe.process_host(batches, out_host)
+            e1.record()                      # after the last D2H, which runs on the compute stream
+            torch.cuda.synchronize()
+            wall.append(time.perf_counter() - t0)
+            dt = e0.elapsed_time(e1) / 1e3   # device time (CUDA events)
             if world > 1:
                 t = torch.tensor([dt], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -404,6 +431,8 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": round(v_u8, 1), "unit": "frames/s",
                "h2d_bytes_per_step": B * EQUI_H * EQUI_W * 3, "d2h_bytes_per_step": B * 2 * fw * 4 * fw * 4,
                "steps": E, "api": "SphericalPipeline.process_host (pinned host uint8 frames -> host saliency maps)",
+               "timing": "CUDA events on the compute stream around the whole call, max over ranks",
+               "wall_clock_value": round(world * B * E / wall[0], 1),
                "f32_host_frames": {"value": round(v_f32, 1), "h2d_bytes_per_step": B * EQUI_H * EQUI_W * 3 * 4}}
     sampler.stop()
     clocks = sampler.summary()
@@ -428,7 +457,8 @@ def run_b200(args, rank, world, local_rank):
                                  % (pipe.bytes_per_frame() * B / 1e9),
                            "algorithmic_bytes_per_frame": pipe.bytes_per_frame()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
-                "roofline": roofline, "kernels": kernels, "tuning": tuning, "cpu_baseline": cpu}
+                "roofline": roofline, "kernels": kernels, "tuning": tuning, "fused_first_site": fused_first,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

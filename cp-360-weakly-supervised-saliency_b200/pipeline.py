@@ -62,7 +62,10 @@ def gather_maps(local_maps, n_total, group=None):
 
 class SphericalPipeline:
     def __init__(self, equi_h=960, equi_w=1920, cube=256, cam_channels=1000, feat_channels=2048,
-                 device=None, seed=1234):
+                 device=None, seed=1234, fuse_first_site=False):
+        """fuse_first_site: run e2c and the CubePad(3) in front of conv1 as ONE kernel
+        (cp360_e2c_cubepad_fwd); the unpadded faces are then never written."""
+        self.fuse_first_site = bool(fuse_first_site)
         if not torch.cuda.is_available():
             raise RuntimeError("SphericalPipeline needs a CUDA device (sm_100a); no CPU fallback")
         if device is None:
@@ -130,7 +133,7 @@ class SphericalPipeline:
 
     # ---------------------------------------------------------------- the step
     def launches_per_step(self):
-        return 1 + len(self.sites) + 2          # e2c, CubePads, -inf fill + c2e_max
+        return 1 + len(self.sites) + 2 - int(self.fuse_first_site)   # e2c, CubePads, -inf fill + c2e_max
 
     def step(self, frames, on_launch=None):
         """frames [B,Hin,Win,3] fp32 (or uint8) on self.device -> sal [B,2fw,4fw] (buffer reused each step).
@@ -144,13 +147,22 @@ class SphericalPipeline:
         n = 6 * self.B
         if on_launch:
             on_launch("e2c", -1)
-        if frames.dtype == torch.uint8:      # decoded video frames: converted as float32(u8)/255 on the fly
+        first = 0
+        if self.fuse_first_site:
+            p = self.sites[0][2]
+            chk(lib.cp360_e2c_cubepad_fwd(frames.data_ptr(), int(frames.dtype == torch.uint8), self._packed.data_ptr(),
+                                          self.site_out[0].data_ptr(), self.B, self.equi_h, self.equi_w, 3, self.cube,
+                                          p, p, p, p, 255.0, None, None, st))
+            first = 1
+        elif frames.dtype == torch.uint8:    # decoded video frames: converted as float32(u8)/255 on the fly
             chk(lib.cp360_e2c_fwd_u8(frames.data_ptr(), self._packed.data_ptr(), self.faces.data_ptr(), self.B,
                                      self.equi_h, self.equi_w, 3, self.cube, _lib.LAYOUT_NCHW, 255.0, None, None, st))
         else:
             chk(lib.cp360_e2c_fwd(frames.data_ptr(), self._packed.data_ptr(), self.faces.data_ptr(), self.B,
                                   self.equi_h, self.equi_w, 3, self.cube, _lib.LAYOUT_NCHW, None, None, st))
         for i, (C, H, p) in enumerate(self.sites):
+            if i < first:
+                continue
             if on_launch:
                 on_launch("cubepad", i)
             chk(lib.cp360_cubepad_fwd(self.site_in[i].data_ptr(), self.site_out[i].data_ptr(), n, C, H, H,

@@ -125,6 +125,20 @@ def main():
             report("e2c 1920x960 -> %d NCHW+norm B=%d" % (w, B), nb,
                    timeit(lambda: e2c.to_cube_tensor(frames, out=out, mean=[.485, .456, .406], std=[.229, .224, .225]),
                           args.iters, flush))
+            # row f2: e2c + norm + CubePad(3) — two kernels vs the fused one (bytes = e2c + CubePad(3) algorithmic)
+            pad3 = cp360_b200.CubePad(3)
+            padded = torch.empty(6 * B, 3, w + 6, w + 6, device=dev)
+            nb2 = nb + 6 * B * 3 * (w * w + (w + 6) ** 2) * 4
+            u8 = torch.randint(0, 256, (B, 960, 1920, 3), dtype=torch.uint8, device=dev)
+            report("e2c+norm -> CubePad(3) %d two kernels B=%d" % (w, B), nb2,
+                   timeit(lambda: pad3(e2c.to_cube_tensor(frames, out=out, mean=[.485, .456, .406], std=[.229, .224, .225])),
+                          args.iters, flush))
+            report("e2c+norm+CubePad(3) %d fused B=%d" % (w, B), nb2,
+                   timeit(lambda: e2c.to_padded_cube_tensor(frames, 3, mean=[.485, .456, .406], std=[.229, .224, .225], out=padded),
+                          args.iters, flush))
+            report("e2c+norm+CubePad(3) %d fused, uint8 frames B=%d" % (w, B), nb2,
+                   timeit(lambda: e2c.to_padded_cube_tensor(u8, 3, mean=[.485, .456, .406], std=[.229, .224, .225], out=padded),
+                          args.iters, flush))
 
     if args.only in ("", "c2e"):
         for w, C in ((8, 1000), (8, 2048), (7, 1000), (16, 256), (64, 64), (256, 8)):
@@ -135,6 +149,8 @@ def main():
                    timeit(lambda: c2e.to_equi_nn(x), args.iters, flush))
             report("c2e+max  [%d,%d,%d,%d]" % (6 * bb, C, w, w), bb * (C * 6 * w * w * 4 + 8 * w * w * 4),
                    timeit(lambda: c2e.to_equi_max(x), args.iters, flush))
+            report("c2e cubic [%d,%d,%d,%d]" % (6 * bb, C, w, w), bb * C * 14 * w * w * 4,
+                   timeit(lambda: c2e.to_equi_cv2(x), args.iters, flush))
     if args.json:
         with open(args.json, "w") as f:
             json.dump(rows, f, indent=1)
