@@ -61,6 +61,14 @@ class CpuChain:
         import torch
         from oracle import ref_port
         from cp360_b200.pipeline import resnet50_cubepad_sites
+        # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+        # would otherwise pin the reference's torch ops to one core
+        try:
+            n_cpu = len(os.sched_getaffinity(0))
+        except Exception:
+            n_cpu = os.cpu_count() or 1
+        if torch.get_num_threads() < n_cpu:
+            torch.set_num_threads(n_cpu)
         self.np, self.torch = np, torch
         self.sites = resnet50_cubepad_sites(CUBE) + [(FEAT_C, CUBE // 32, 1)]
         self.e2c = ref_port.Equi2CubePort(CUBE, EQUI_H, EQUI_W)

@@ -630,7 +630,8 @@ static bool row_plan(const CubePadGeom& g, int64_t n_planes, int C, RowArgs* a) 
   const char* order_env = getenv("CP360_ROW_ORDER");
   a->order = (order_env && *order_env) ? atoi(order_env)
              : (t_tune && t_tune->row_order1 > 0) ? t_tune->row_order1 - 1 : (a->nb >= 8 ? 0 : 2);
-  if (a->order != 0 && a->order != 2 && a->order != 3) a->order = 4;
+  if (a->order != 0 && a->order != 2 && a->order != 3 && a->order != 5) a->order = 4;
+  a->n_static = 0;
   a->draw = std::min(16, std::max(1, env_int("CP360_ROW_DRAW", 2)));
   a->work = nullptr;
   a->out_C = C; a->out_coff = 0; a->scale = nullptr; a->shift = nullptr; a->relu = 0;
@@ -677,6 +678,12 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
   const int64_t ctas_needed = ((int64_t)a.n_units + kRowWarps - 1) / kRowWarps;
   const int64_t grid = std::min<int64_t>(ctas_needed, (int64_t)sm_count() * per_sm);
+  if (a.order == 5) {
+    // whole static rounds over the grid's warps first, the last ~tail % of the units dynamically
+    const int64_t gw = grid * kRowWarps;
+    const int64_t keep = (int64_t)a.n_units * (100 - std::min(100, std::max(0, env_int("CP360_ROW_TAIL_PCT", 12)))) / 100;
+    a.n_static = (int32_t)(keep / gw * gw);
+  }
   launch_kernel(kern, (unsigned)grid, kRowThreads, smem_req, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;

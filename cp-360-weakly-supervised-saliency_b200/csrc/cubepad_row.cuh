@@ -90,6 +90,8 @@ struct RowArgs {
                             //    draw groups of 8 consecutive units from the grid-wide counter, their warps draw
                             //    from the CTA's current group
   int32_t draw;
+  int32_t n_static;         // order 5: units below this index are dealt like order 2, the rest (the tail of the
+                            //    launch) are drawn one at a time from the grid-wide counter by whichever warp is free
   // output tensor may have more channels than the input (CubePad of a channel-concatenation, written
   // one source at a time: model/clstm.py:57-58): output plane of (face-in-batch nf, channel c) is
   // nf * out_C + out_coff + c
@@ -239,6 +241,14 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     } else if (a.order == 2) {
       const int k = atomicAdd(ctr, 1);
       u = (k >> 3) * GW + blockIdx.x * kRowWarps + (k & 7);
+    } else if (a.order == 5) {
+      u = a.n_units;
+      if (!u_left) {                                   // u_left doubles as "this warp is in the tail"
+        const int k = atomicAdd(ctr, 1);
+        u = (k >> 3) * GW + blockIdx.x * kRowWarps + (k & 7);
+        if (u >= a.n_static) u_left = 1;
+      }
+      if (u_left) u = a.n_static + (int)min(atomicAdd(a.work, 1u), (uint32_t)(a.n_units - a.n_static));
     } else {
       u = gw + my_k * GW;
       ++my_k;
