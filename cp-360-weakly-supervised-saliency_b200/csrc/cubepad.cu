@@ -330,50 +330,39 @@ cubepad_cube_kernel(const CubeArgs a, const __grid_constant__ CubePadGeom g) {
 }
 
 // ------------------------------------------------------------------------------------------
-// backward (fp32): interior copy, then halo scatter-add
+// backward (fp32): one pass, no atomics. A thread owns one INPUT pixel: it takes the gradient of
+// the interior copy and, if the pixel lies within a pad width of a face edge, adds the gradients of
+// the halo positions that copied it (cubepad_for_each_copy: the push table inverted), in a fixed
+// order — the result is reproducible bit for bit from run to run.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-cubepad_bwd_interior_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t n_planes,
-                            const __grid_constant__ CubePadGeom g) {
+cubepad_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t total, int C,
+                   const __grid_constant__ CubePadGeom g, FastDiv d_HW, FastDiv d_W, FastDiv d_C) {
   const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
-  for (int64_t plane = blockIdx.y; plane < n_planes; plane += gridDim.y) {
-    const float* src = gy + plane * HoWo + g.pt * g.Wo + g.pl;
-    float* dst = gx + plane * HW;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HW; e += gridDim.x * blockDim.x) {
-      const int yy = e / g.W, xx = e - yy * g.W;
-      dst[e] = src[yy * g.Wo + xx];
+  const int pmax = max(max(g.pl, g.pr), max(g.pt, g.pd));
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= total) break;
+    // planes < 2^31 (validated on the host): split the 64-bit index once per block-stride step
+    const int64_t plane_blk = i0 / HW;
+    const int rem = (int)(i - plane_blk * HW);                    // < HW + 256
+    const int dp = fdiv(rem, d_HW);
+    const int plane = (int)plane_blk + dp;
+    const int e = rem - dp * HW;
+    const int y = fdiv(e, d_W), x = e - y * g.W;
+    const float* src = gy + (int64_t)plane * HoWo;
+    float acc = src[(y + g.pt) * g.Wo + x + g.pl];
+    if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) < pmax) {
+      const int nf = fdiv(plane, d_C);
+      const int c = plane - nf * C;
+      const int f = nf % 6;
+      const float* cube = gy + ((int64_t)(nf - f) * C + c) * HoWo;
+      const int64_t fstride = (int64_t)C * HoWo;
+      cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
+        acc += __ldg(cube + dface * fstride + oy * g.Wo + ox);
+      });
     }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-cubepad_bwd_halo_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t n_planes,
-                        int C, const __grid_constant__ CubePadGeom g) {
-  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
-  const int n_top = g.pt * g.Wo, lr = g.pl + g.pr, n_mid = g.H * lr;
-  const int n_halo = HoWo - HW;
-  const int64_t face_stride = (int64_t)C * HW;
-  for (int64_t plane = blockIdx.y; plane < n_planes; plane += gridDim.y) {
-    const int64_t nf = plane / C;
-    const int c = (int)(plane - nf * C);
-    const int f = (int)(nf % 6);
-    float* cube = gx + ((nf - f) * C + c) * HW;
-    const float* src = gy + plane * HoWo;
-    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < n_halo; h += gridDim.x * blockDim.x) {
-      int oy, ox;
-      if (h < n_top) {
-        oy = h / g.Wo; ox = h - oy * g.Wo;
-      } else if (h < n_top + n_mid) {
-        const int q = h - n_top, r = q / lr, cc = q - r * lr;
-        oy = g.pt + r; ox = cc < g.pl ? cc : g.W + cc;
-      } else {
-        const int q = h - n_top - n_mid, r = q / g.Wo;
-        oy = g.pt + g.H + r; ox = q - r * g.Wo;
-      }
-      int sf;
-      const int pix = cubepad_src(g, f, oy, ox, &sf);
-      atomicAdd(cube + sf * face_stride + pix, src[oy * g.Wo + ox]);
-    }
+    gx[i] = acc;
   }
 }
 
@@ -1009,6 +998,29 @@ int cp360_cubepad_fused_fwd(const float* x, float* y, int64_t n_faces, int64_t C
   return rc;
 }
 
+int cp360_cubepad_build_inverse_map(int H, int W, int pl, int pr, int pt, int pd, int32_t* offsets_host,
+                                    int32_t* entries_host) {
+  CubePadGeom g;
+  CP360_CHECK_ARG(make_geom(H, W, pl, pr, pt, pd, &g), CP360_ERR_SHAPE,
+                  "CubePad needs square faces and 0 <= pad <= H (H=%d W=%d pads l%d r%d t%d d%d)", H, W, pl, pr, pt, pd);
+  CP360_CHECK_ARG(offsets_host != nullptr, CP360_ERR_BAD_ARG, "null offsets");
+  const int HoWo = g.Ho * g.Wo;
+  int32_t n = 0;
+  for (int f = 0; f < 6; ++f)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        offsets_host[(f * H + y) * W + x] = n;
+        if (entries_host) entries_host[n] = f * HoWo + (y + pt) * g.Wo + x + pl;      // the interior copy
+        ++n;
+        cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
+          if (entries_host) entries_host[n] = dface * HoWo + oy * g.Wo + ox;
+          ++n;
+        });
+      }
+  offsets_host[6 * H * W] = n;
+  return CP360_OK;
+}
+
 int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C, int H, int W,
                           int pl, int pr, int pt, int pd, void* stream) {
   CubePadGeom g;
@@ -1019,15 +1031,13 @@ int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C
   if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_planes = n_faces * C;
-  const int HW = g.H * g.W, n_halo = g.Ho * g.Wo - HW;
-  dim3 grid((unsigned)std::min(64, (HW + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
-  cubepad_bwd_interior_kernel<<<grid, 256, 0, st>>>(gy, gx, n_planes, g);
+  const int HW = g.H * g.W;
+  CP360_CHECK_ARG(n_planes <= 0x7fffffff - 1, CP360_ERR_RANGE, "too many planes");
+  const int64_t total = n_planes * HW;
+  const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
+  cubepad_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, (int)C, g, make_fastdiv((uint32_t)HW),
+                                                        make_fastdiv((uint32_t)g.W), make_fastdiv((uint32_t)C));
   CP360_LAUNCHED();
-  if (n_halo > 0) {
-    dim3 grid2((unsigned)std::min(64, (n_halo + 255) / 256), (unsigned)std::min<int64_t>(n_planes, 65535));
-    cubepad_bwd_halo_kernel<<<grid2, 256, 0, st>>>(gy, gx, n_planes, (int)C, g);
-    CP360_LAUNCHED();
-  }
   return CP360_OK;
 }
 

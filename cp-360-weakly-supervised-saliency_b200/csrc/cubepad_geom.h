@@ -177,4 +177,41 @@ CP360_HD int32_t cubepad_src(const CubePadGeom& g, int f, int oy, int ox, int* s
   return m.base + m.sr * r + m.sc * c;
 }
 
+// The transpose of the map above (backward pass, tests): calls fn(dface, oy, ox) for every HALO
+// output position of the cube that copies source pixel (f, y, x) — the four push entries of face f
+// inverted. Entry e covers destination (u, v) in [0,U) x [0,V) with
+//   cmode 0: r = u, c = clamp(v + off, 0, W-1);   cmode 1: r = clamp(u + off, 0, H-1), c = v
+//   y' = yr*r + yc*c + y0,  x' = xr*r + xc*c + x0   (a signed permutation: one of yr, yc is +-1)
+// so (r, c) follows from (y, x) directly and a clamped coordinate at 0 / its maximum stands for the
+// whole run of corner positions that replicate it. Positions are visited in a fixed order
+// (entry, u, v ascending), which makes a sum over them reproducible.
+template <class F>
+CP360_HD void cubepad_for_each_copy(const CubePadGeom& g, int f, int y, int x, F&& fn) {
+  for (int e = 0; e < 4; ++e) {
+    const PushEntry& pe = g.push[f][e];
+    if (pe.U <= 0 || pe.V <= 0) continue;
+    int r, c;
+    if (pe.yr != 0) { r = (y - pe.y0) * pe.yr; c = (x - pe.x0) * pe.xc; }
+    else { c = (y - pe.y0) * pe.yc; r = (x - pe.x0) * pe.xr; }
+    int ulo, uhi, vlo, vhi;
+    if (pe.cmode == 0) {
+      if (r < 0 || r >= pe.U || c < 0 || c > g.W - 1) continue;
+      ulo = uhi = r;
+      vlo = c == 0 ? 0 : c - pe.off;
+      vhi = c == g.W - 1 ? pe.V - 1 : c - pe.off;
+    } else {
+      if (c < 0 || c >= pe.V || r < 0 || r > g.H - 1) continue;
+      vlo = vhi = c;
+      ulo = r == 0 ? 0 : r - pe.off;
+      uhi = r == g.H - 1 ? pe.U - 1 : r - pe.off;
+    }
+    if (ulo < 0) ulo = 0;
+    if (vlo < 0) vlo = 0;
+    if (uhi > pe.U - 1) uhi = pe.U - 1;
+    if (vhi > pe.V - 1) vhi = pe.V - 1;
+    for (int u = ulo; u <= uhi; ++u)
+      for (int v = vlo; v <= vhi; ++v) fn(pe.dface, pe.oy0 + u, pe.ox0 + v);
+  }
+}
+
 }  // namespace cp360

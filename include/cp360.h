@@ -106,9 +106,19 @@ CP360_API int cp360_cubepad_fused_fwd(const float* x_dev, float* y_dev, int64_t 
 CP360_API int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,
                             char* buf, int buf_len);
 
+/* Host: the transpose of cp360_cubepad_build_map in CSR form. For source pixel s = (face*H + y)*W + x of
+ * one channel's cube, entries_host[offsets_host[s] .. offsets_host[s+1]) are the flat output indices
+ * (face'*Ho*Wo + oy*Wo + ox) that copy it: the interior copy first, then the halo copies in the order
+ * cp360_cubepad_bwd_f32 sums them. offsets_host[6*H*W + 1]; entries_host[6*Ho*Wo] (every output pixel
+ * appears exactly once) or NULL to only count. */
+CP360_API int cp360_cubepad_build_inverse_map(int H, int W, int pl, int pr, int pt, int pd, int32_t* offsets_host,
+                                    int32_t* entries_host);
+
 /* Device, fp32: gx[6N,C,H,W] = dCubePad^T(gy[6N,C,Ho,Wo]) — every input pixel receives the sum
  * of the gradients of all output pixels that copied it (what autograd derives from the
- * cat/index_select/repeat chain; needed by temporal_model/train_temporal.py:167-170). */
+ * cat/index_select/repeat chain; needed by temporal_model/train_temporal.py:167-170). One pass, no
+ * atomics: the sum runs in the fixed order of cp360_cubepad_build_inverse_map, so gradients are
+ * reproducible bit for bit. */
 CP360_API int cp360_cubepad_bwd_f32(const float* gy_dev, float* gx_dev, int64_t n_faces, int64_t C, int H,
                           int W, int pl, int pr, int pt, int pd, void* stream);
 

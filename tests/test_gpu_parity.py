@@ -253,7 +253,8 @@ def test_cubepad_errors_and_edge_cases(dev):
 
 def test_cubepad_backward_matches_autograd(dev):
     """Backward = transpose of the gather (train_temporal.py:167-170 back-propagates through it)."""
-    for shape, pad in [((6, 3, 7, 7), 1), ((12, 4, 8, 8), [2, 1, 1, 3]), ((6, 2, 32, 32), 3)]:
+    for shape, pad in [((6, 3, 7, 7), 1), ((12, 4, 8, 8), [2, 1, 1, 3]), ((6, 2, 32, 32), 3), ((6, 5, 9, 9), [4, 2, 3, 5]),
+                       ((12, 2000, 7, 7), 1), ((6, 3, 5, 5), 5), ((6, 2, 56, 56), 1), ((6, 1, 1, 1), 1)]:
         x = torch.randn(shape, device=dev, dtype=torch.float32, requires_grad=True)
         y = cp360_b200.CubePad(pad)(x)
         gy = torch.randn_like(y)
@@ -261,6 +262,14 @@ def test_cubepad_backward_matches_autograd(dev):
         x2 = x.detach().clone().requires_grad_(True)
         gather_reference(x2, ocp.index_map(shape[2], shape[3], pad)).backward(gy)
         torch.testing.assert_close(x.grad, x2.grad, rtol=0, atol=1e-5)
+        # one pass, fixed summation order: bit-reproducible, and exact on integer-valued gradients
+        g1 = cp360_b200.cube_pad.cubepad_backward(gy, cp360_b200.get_pad_size(pad), shape[2:])
+        g2 = cp360_b200.cube_pad.cubepad_backward(gy, cp360_b200.get_pad_size(pad), shape[2:])
+        assert torch.equal(g1, g2)
+        ones = cp360_b200.cube_pad.cubepad_backward(torch.ones_like(y), cp360_b200.get_pad_size(pad), shape[2:])
+        mult = np.bincount(ocp.index_map(shape[2], shape[3], pad).reshape(-1), minlength=6 * shape[2] * shape[3])
+        want = np.broadcast_to(mult.reshape(1, 6, 1, shape[2], shape[3]), (shape[0] // 6, 6, shape[1], shape[2], shape[3]))
+        np.testing.assert_array_equal(ones.cpu().numpy().reshape(shape[0] // 6, 6, shape[1], shape[2], shape[3]), want)
 
 
 def test_cubepad_is_stream_ordered(dev):

@@ -152,3 +152,27 @@ def test_c2e_cubic_errors():
     assert lib.cp360_c2e_build_cubic_plan(513, buf.ctypes.data) == 4
     assert lib.cp360_c2e_cubic_fwd(None, None, None, 1, 4, 8, None) == 1       # null pointers
     assert lib.cp360_c2e_cubic_fwd(None, None, None, 0, 4, 8, None) == 0       # empty batch
+
+
+@pytest.mark.parametrize("H,pad", [(1, 1), (2, 1), (2, 2), (3, 3), (4, 1), (7, 1), (8, 3), (5, 2), (6, [1, 2, 3, 0]),
+                                   (6, [2, 1, 1, 3]), (7, [3, 3, 1, 1]), (7, [1, 1, 3, 3]), (5, [0, 2, 1, 0]),
+                                   (5, [2, 0, 0, 1]), (5, [0, 0, 2, 2]), (4, [0, 0, 0, 0]), (9, [4, 2, 3, 5]),
+                                   (9, [9, 9, 9, 9]), (32, 3), (56, 1)])
+def test_cubepad_inverse_map_is_transpose_of_forward_map(H, pad):
+    """cp360_cubepad_build_inverse_map (what the backward kernel sums over) is exactly the transpose
+    of the forward index map: every output pixel appears once, under the source it copies."""
+    pl, pr, pt, pd = cp360_b200.get_pad_size(pad)
+    fwd = cp360_b200.cubepad_index_map(H, H, pad).reshape(-1)                  # [6*Ho*Wo] -> source index
+    n_src, n_out = 6 * H * H, fwd.size
+    offs = np.empty(n_src + 1, dtype=np.int32)
+    ents = np.full(n_out, -1, dtype=np.int32)
+    _lib.check(_lib.lib().cp360_cubepad_build_inverse_map(H, H, pl, pr, pt, pd, offs.ctypes.data, ents.ctypes.data))
+    assert offs[0] == 0 and offs[-1] == n_out
+    assert np.array_equal(np.sort(ents), np.arange(n_out))                     # a permutation of the outputs
+    src_of_entry = np.repeat(np.arange(n_src), np.diff(offs))
+    np.testing.assert_array_equal(fwd[ents], src_of_entry)
+    np.testing.assert_array_equal(np.diff(offs), np.bincount(fwd, minlength=n_src))
+    # count-only form
+    offs2 = np.empty_like(offs)
+    _lib.check(_lib.lib().cp360_cubepad_build_inverse_map(H, H, pl, pr, pt, pd, offs2.ctypes.data, None))
+    np.testing.assert_array_equal(offs, offs2)

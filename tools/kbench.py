@@ -151,6 +151,20 @@ def main():
                    timeit(lambda: c2e.to_equi_max(x), args.iters, flush))
             report("c2e cubic [%d,%d,%d,%d]" % (6 * bb, C, w, w), bb * C * 14 * w * w * 4,
                    timeit(lambda: c2e.to_equi_cv2(x), args.iters, flush))
+    if args.only in ("", "bwd"):
+        # row f1: the training path's backward kernels (train_temporal.py:105-107,167-170)
+        for C, H, p in ((64, 128, 1), (256, 32, 1), (2048, 8, 1), (2000, 7, 1), (4000, 7, 1)):
+            n = 6 * B
+            gy = torch.randn(n, C, H + 2 * p, H + 2 * p, device=dev)
+            nbytes = n * C * (H * H + (H + 2 * p) ** 2) * 4
+            report("cubepad bwd [%d,%d,%d,%d] p%d" % (n, C, H, H, p), nbytes,
+                   timeit(lambda: cp360_b200.cube_pad.cubepad_backward(gy, (p, p, p, p), (H, H)), args.iters, flush))
+            del gy
+        for w, C in ((7, 1000), (8, 1000)):
+            c2e = cp360_b200.Cube2Equi(w)
+            g = torch.randn(B, C, 2 * w, 4 * w, device=dev)
+            report("c2e bwd  [%d,%d,%d,%d]" % (B, C, 2 * w, 4 * w), B * C * 14 * w * w * 4,
+                   timeit(lambda: c2e._backward(g), args.iters, flush))
     if args.json:
         with open(args.json, "w") as f:
             json.dump(rows, f, indent=1)
