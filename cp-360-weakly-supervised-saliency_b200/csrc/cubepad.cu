@@ -330,39 +330,64 @@ cubepad_cube_kernel(const CubeArgs a, const __grid_constant__ CubePadGeom g) {
 }
 
 // ------------------------------------------------------------------------------------------
-// backward (fp32): one pass, no atomics. A thread owns one INPUT pixel: it takes the gradient of
-// the interior copy and, if the pixel lies within a pad width of a face edge, adds the gradients of
-// the halo positions that copied it (cubepad_for_each_copy: the push table inverted), in a fixed
-// order — the result is reproducible bit for bit from run to run.
+// backward (fp32), no atomics. Only pixels within a pad width of a face edge are copied by halo
+// positions, so the work is split by kind rather than mixed inside warps:
+//   cubepad_bwd_inner_kernel   every pixel outside that band: gx = gy of its interior copy (a
+//                              shifted, fully coalesced copy)
+//   cubepad_bwd_band_kernel    a thread per band pixel: interior copy + the gradients of the halo
+//                              positions that copied it (cubepad_for_each_copy: the push table
+//                              inverted), summed in a fixed order -> bit-reproducible gradients
+// The two kernels write disjoint pixels. BIG: more than 2^31 elements (64-bit index arithmetic).
 // ------------------------------------------------------------------------------------------
+template <bool BIG>
 __global__ void __launch_bounds__(256)
-cubepad_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t total, int C,
-                   const __grid_constant__ CubePadGeom g, FastDiv d_HW, FastDiv d_W, FastDiv d_C) {
+cubepad_bwd_inner_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t total,
+                         const __grid_constant__ CubePadGeom g, int pm, FastDiv d_HW, FastDiv d_W) {
   const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
-  const int pmax = max(max(g.pl, g.pr), max(g.pt, g.pd));
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = i0 + threadIdx.x;
-    if (i >= total) break;
-    // planes < 2^31 (validated on the host): split the 64-bit index once per block-stride step
-    const int64_t plane_blk = i0 / HW;
-    const int rem = (int)(i - plane_blk * HW);                    // < HW + 256
-    const int dp = fdiv(rem, d_HW);
-    const int plane = (int)plane_blk + dp;
-    const int e = rem - dp * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t plane;
+    int e;
+    if (BIG) { plane = i / HW; e = (int)(i - plane * HW); }
+    else { const int p32 = fdiv((int)i, d_HW); plane = p32; e = (int)i - p32 * HW; }
     const int y = fdiv(e, d_W), x = e - y * g.W;
-    const float* src = gy + (int64_t)plane * HoWo;
-    float acc = src[(y + g.pt) * g.Wo + x + g.pl];
-    if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) < pmax) {
-      const int nf = fdiv(plane, d_C);
-      const int c = plane - nf * C;
-      const int f = nf % 6;
-      const float* cube = gy + ((int64_t)(nf - f) * C + c) * HoWo;
-      const int64_t fstride = (int64_t)C * HoWo;
-      cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
-        acc += __ldg(cube + dface * fstride + oy * g.Wo + ox);
-      });
+    if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) >= pm)
+      gx[i] = __ldcs(gy + plane * HoWo + (y + g.pt) * g.Wo + x + g.pl);
+  }
+}
+
+template <bool BIG>
+__global__ void __launch_bounds__(256)
+cubepad_bwd_band_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t total, int C,
+                        const __grid_constant__ CubePadGeom g, int pm, int nb, FastDiv d_nb, FastDiv d_W,
+                        FastDiv d_2pm, FastDiv d_C) {
+  const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+  const bool all = 2 * pm >= g.H;                       // the band covers the whole face
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t plane;
+    int t;
+    if (BIG) { plane = i / nb; t = (int)(i - plane * nb); }
+    else { const int p32 = fdiv((int)i, d_nb); plane = p32; t = (int)i - p32 * nb; }
+    int y, x;
+    if (all || t < 2 * pm * g.W) {                      // top pm rows, then bottom pm rows: lanes along x
+      y = fdiv(t, d_W);
+      x = t - y * g.W;
+      if (!all && y >= pm) y += g.H - 2 * pm;
+    } else {                                            // left / right pm columns of the rows in between
+      const int q = t - 2 * pm * g.W;
+      const int row = fdiv(q, d_2pm), col = q - row * 2 * pm;
+      y = pm + row;
+      x = col < pm ? col : g.W - 2 * pm + col;
     }
-    gx[i] = acc;
+    const int64_t nf = BIG ? plane / C : (int64_t)fdiv((int)plane, d_C);
+    const int c = (int)(plane - nf * C);
+    const int f = (int)(nf % 6);
+    float acc = __ldg(gy + plane * HoWo + (y + g.pt) * g.Wo + x + g.pl);
+    const float* cube = gy + ((nf - f) * C + c) * HoWo;
+    const int64_t fstride = (int64_t)C * HoWo;
+    cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
+      acc += __ldg(cube + dface * fstride + oy * g.Wo + ox);
+    });
+    gx[plane * HW + y * g.W + x] = acc;
   }
 }
 
@@ -1032,12 +1057,25 @@ int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_planes = n_faces * C;
   const int HW = g.H * g.W;
-  CP360_CHECK_ARG(n_planes <= 0x7fffffff - 1, CP360_ERR_RANGE, "too many planes");
-  const int64_t total = n_planes * HW;
-  const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
-  cubepad_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, (int)C, g, make_fastdiv((uint32_t)HW),
-                                                        make_fastdiv((uint32_t)g.W), make_fastdiv((uint32_t)C));
-  CP360_LAUNCHED();
+  const int pm = std::max(std::max(g.pl, g.pr), std::max(g.pt, g.pd));
+  const int nb = 2 * pm >= g.H ? HW : HW - (g.H - 2 * pm) * (g.W - 2 * pm);     // band pixels per plane
+  const int64_t total = n_planes * HW, total_b = n_planes * nb;
+  const bool big = total >= 0x7fffffff || n_planes * (int64_t)(g.Ho * g.Wo) >= 0x7fffffff;
+  const FastDiv d_HW = make_fastdiv((uint32_t)HW), d_W = make_fastdiv((uint32_t)g.W);
+  if (nb < HW) {
+    const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    if (big) cubepad_bwd_inner_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);
+    else cubepad_bwd_inner_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);
+    CP360_LAUNCHED();
+  }
+  if (nb > 0) {
+    const int64_t blocks = std::min<int64_t>((total_b + 255) / 256, (int64_t)sm_count() * 16);
+    const FastDiv d_nb = make_fastdiv((uint32_t)nb), d_2pm = make_fastdiv((uint32_t)std::max(1, 2 * pm)),
+                  d_C = make_fastdiv((uint32_t)C);
+    if (big) cubepad_bwd_band_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total_b, (int)C, g, pm, nb, d_nb, d_W, d_2pm, d_C);
+    else cubepad_bwd_band_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total_b, (int)C, g, pm, nb, d_nb, d_W, d_2pm, d_C);
+    CP360_LAUNCHED();
+  }
   return CP360_OK;
 }
 

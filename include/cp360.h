@@ -116,8 +116,8 @@ CP360_API int cp360_cubepad_build_inverse_map(int H, int W, int pl, int pr, int 
 
 /* Device, fp32: gx[6N,C,H,W] = dCubePad^T(gy[6N,C,Ho,Wo]) — every input pixel receives the sum
  * of the gradients of all output pixels that copied it (what autograd derives from the
- * cat/index_select/repeat chain; needed by temporal_model/train_temporal.py:167-170). One pass, no
- * atomics: the sum runs in the fixed order of cp360_cubepad_build_inverse_map, so gradients are
+ * cat/index_select/repeat chain; needed by temporal_model/train_temporal.py:167-170). No atomics
+ * (a copy kernel for the face interiors, a gather kernel for the pixels halo positions copy): the sum runs in the fixed order of cp360_cubepad_build_inverse_map, so gradients are
  * reproducible bit for bit. */
 CP360_API int cp360_cubepad_bwd_f32(const float* gy_dev, float* gx_dev, int64_t n_faces, int64_t C, int H,
                           int W, int pl, int pr, int pt, int pd, void* stream);
