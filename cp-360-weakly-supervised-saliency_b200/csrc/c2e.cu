@@ -90,6 +90,13 @@ c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
 // are the inner loop, so the plan entry lives in registers and the cube is read from DRAM
 // exactly once through six bulk copies.
 constexpr int kC2eSmallThreads = 512;
+// Bank skew of the staged faces: a warp covers 32 consecutive pixels of an equirect row, i.e. runs of
+// ~w pixels on up to four faces (B L F R around the equator) that sample the SAME face row; with
+// every face at a multiple of 32 words those runs collide in the same banks (4-way conflicts at
+// w = 8). Offsetting the equatorial faces by 0 / 8 / 16 / 24 words (16 B multiples, as the bulk
+// copies need) spreads them over all 32 banks.
+__device__ __constant__ int kFaceSkew[6] = {0 /*B*/, 4 /*D*/, 8 /*F*/, 16 /*L*/, 24 /*R*/, 28 /*T*/};   // non-decreasing: regions stay disjoint
+constexpr int kFaceSkewMax = 32;
 
 template <int MODE>
 __global__ void __launch_bounds__(kC2eSmallThreads)
@@ -114,7 +121,7 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
     tma::mbar_expect_tx(bar, 6u * bytes);
 #pragma unroll
     for (int f = 0; f < 6; ++f)
-      tma::bulk_load(cs + (size_t)f * kch * ww, cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
+      tma::bulk_load(cs + (size_t)f * kch * ww + kFaceSkew[f], cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
   }
   __syncthreads();
   tma::mbar_wait(bar, 0);
@@ -129,7 +136,7 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
               ys = ys_ok ? t.y0 + 1 : 0;
     const bool nw_ok = xw_ok && yn_ok, ne_ok = xe_ok && yn_ok, sw_ok = xw_ok && ys_ok,
                se_ok = xe_ok && ys_ok;
-    const float* src = cs + (size_t)t.face * kch * ww;
+    const float* src = cs + (size_t)t.face * kch * ww + kFaceSkew[t.face];
     const int o_nw = yn * w + xw, o_ne = yn * w + xe, o_sw = ys * w + xw, o_se = ys * w + xe;
     float best = -INFINITY;
     float* dst = out + ((int64_t)b * C + c0) * P + pix;
@@ -275,13 +282,13 @@ c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restric
     tma::mbar_expect_tx(bar, 6u * bytes);
 #pragma unroll
     for (int f = 0; f < 6; ++f)
-      tma::bulk_load(cs + (size_t)f * kch * ww, cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
+      tma::bulk_load(cs + (size_t)f * kch * ww + kFaceSkew[f], cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
   }
   __syncthreads();
   tma::mbar_wait(bar, 0);
   for (int pix = tid; pix < P; pix += kC2eSmallThreads) {
     const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
-    cubic_pixel(cs + (size_t)t.face * kch * ww, out + ((int64_t)b * C + c0) * P + pix, t, w, ww, P, kl);
+    cubic_pixel(cs + (size_t)t.face * kch * ww + kFaceSkew[t.face], out + ((int64_t)b * C + c0) * P + pix, t, w, ww, P, kl);
   }
 }
 
@@ -324,7 +331,7 @@ static int small_plan(const void* cube, int64_t C, int w, size_t* smem) {
   k = (int)std::min<int64_t>(k, C);
   k -= k % q;
   if (k < q) return 0;
-  *smem = 128 + (size_t)6 * k * ww * 4;
+  *smem = 128 + (size_t)6 * k * ww * 4 + kFaceSkewMax * 4;
   return k;
 }
 
@@ -342,7 +349,7 @@ static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts,
     while (k > 4 * q && B * ((C + k - 1) / k) < 2 * (int64_t)sm_count()) {
       k = std::max(q, (k / 2) - ((k / 2) % q));
     }
-    smem = 128 + (size_t)6 * k * ww * 4;
+    smem = 128 + (size_t)6 * k * ww * 4 + kFaceSkewMax * 4;
     const int groups = (int)((C + k - 1) / k);
     CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
     auto kern = c2e_small_kernel<MODE>;
@@ -406,7 +413,7 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
     int q = 1;
     while ((q * ww) % 4) q <<= 1;
     while (k > 4 * q && B * ((C + k - 1) / k) < 2 * (int64_t)sm_count()) k = std::max(q, (k / 2) - ((k / 2) % q));
-    smem = 128 + (size_t)6 * k * ww * 4;
+    smem = 128 + (size_t)6 * k * ww * 4 + kFaceSkewMax * 4;
     const int groups = (int)((C + k - 1) / k);
     CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
     CP360_CUDA_OK(cudaFuncSetAttribute(c2e_cubic_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
