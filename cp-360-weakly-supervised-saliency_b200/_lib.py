@@ -35,6 +35,8 @@ SIGNATURES = {
     "cp360_c2e_build_plan": (c_i32, [c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp360_c2e_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
     "cp360_c2e_max_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "cp360_c2e_max_arg_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "cp360_c2e_max_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
     "cp360_c2e_build_cubic_plan": (c_i32, [c_i32, c_vp]),
     "cp360_c2e_cubic_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
     "cp360_c2e_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),

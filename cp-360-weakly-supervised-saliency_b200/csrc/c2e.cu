@@ -39,6 +39,28 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// (value, channel) keys for the arg-max variant: order-preserving map of the float into the high word,
+// ~channel in the low word, so a 64-bit atomicMax keeps the largest value and, among equal values,
+// the LOWEST channel (torch.max(dim) returns the first maximal index). Every key is > 0.
+__device__ __forceinline__ unsigned long long argmax_key(float v, int c) {
+  v += 0.0f;
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)o << 32) | (uint32_t)(0xffffffffu - (uint32_t)c);
+}
+
+__global__ void c2e_argmax_decode_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ sal,
+                                         int32_t* __restrict__ arg, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const uint32_t o = (uint32_t)(k >> 32);
+    sal[i] = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+    arg[i] = (int32_t)(0xffffffffu - (uint32_t)k);
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
   pdl_trigger();
   pdl_wait();
@@ -49,7 +71,8 @@ __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
 
 constexpr int kC2eThreads = 256;
 
-// MODE 0: write equi[B,C,P]; MODE 1: channel max into sal[B,P]
+// MODE 0: write equi[B,C,P]; MODE 1: channel max into sal[B,P]; MODE 2: (max, arg-max channel) keys
+// into a uint64 [B,P] scratch (decoded by c2e_argmax_decode_kernel)
 template <int MODE>
 __global__ void __launch_bounds__(kC2eThreads)
 c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
@@ -71,6 +94,7 @@ c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
   for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
     const float* src = cube + ((b * 6 + t.face) * C + c_begin) * (int64_t)ww + o_nw;
     float best = -INFINITY;
+    int best_c = c_begin;
 #pragma unroll 4
     for (int c = c_begin; c < c_end; ++c, src += ww) {
       float acc = 0.0f;                      // order of torch's grid_sampler CUDA kernel
@@ -79,9 +103,11 @@ c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
       if (sw_ok) acc = fmaf(__ldg(src + w), wt.z, acc);
       if (se_ok) acc = fmaf(__ldg(src + w + 1), wt.w, acc);
       if (MODE == 0) __stcs(out + (b * C + c) * (int64_t)P + pix, acc);
-      else best = fmaxf(best, acc);
+      else if (MODE == 1) best = fmaxf(best, acc);
+      else if (acc > best) { best = acc; best_c = c; }
     }
     if (MODE == 1) atomic_max_float(out + b * (int64_t)P + pix, best);
+    if (MODE == 2) atomicMax(reinterpret_cast<unsigned long long*>(out) + b * (int64_t)P + pix, argmax_key(best, best_c));
   }
 }
 
@@ -139,6 +165,7 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
     const float* src = cs + (size_t)t.face * kch * ww + kFaceSkew[t.face];
     const int o_nw = yn * w + xw, o_ne = yn * w + xe, o_sw = ys * w + xw, o_se = ys * w + xe;
     float best = -INFINITY;
+    int best_c = 0;
     float* dst = out + ((int64_t)b * C + c0) * P + pix;
 #pragma unroll 4
     for (int c = 0; c < kl; ++c, src += ww) {
@@ -148,9 +175,11 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
       if (sw_ok) acc = fmaf(src[o_sw], wt.z, acc);
       if (se_ok) acc = fmaf(src[o_se], wt.w, acc);
       if (MODE == 0) __stcs(dst + (int64_t)c * P, acc);
-      else best = fmaxf(best, acc);
+      else if (MODE == 1) best = fmaxf(best, acc);
+      else if (acc > best) { best = acc; best_c = c; }
     }
     if (MODE == 1) atomic_max_float(out + (int64_t)b * P + pix, best);
+    if (MODE == 2) atomicMax(reinterpret_cast<unsigned long long*>(out) + (int64_t)b * P + pix, argmax_key(best, c0 + best_c));
   }
   CP360_TRACE_T0(3);
 }
@@ -177,6 +206,33 @@ c2e_bwd_kernel(const float* __restrict__ gequi, const uint32_t* __restrict__ tap
       if (xw_ok && ys_ok) atomicAdd(dst + w, g * wt.z);
       if (xe_ok && ys_ok) atomicAdd(dst + w + 1, g * wt.w);
     }
+  }
+}
+
+// Backward of the fused back-projection + channel max: the gradient of sal[b,pix] flows to the four
+// taps of channel arg[b,pix] only (torch.max backward + grid_sample backward,
+// train_temporal.py:105-107). gcube is zero-filled by the caller-side memset of the launch.
+__global__ void __launch_bounds__(kC2eThreads)
+c2e_max_bwd_kernel(const float* __restrict__ gsal, const int32_t* __restrict__ arg,
+                   const uint32_t* __restrict__ taps, const float4* __restrict__ wts,
+                   float* __restrict__ gcube, int64_t B, int C, int w) {
+  const int P = 8 * w * w, ww = w * w;
+  const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
+  if (pix >= P) return;
+  const Tap t = decode_tap(__ldg(taps + pix));
+  const float4 wt = __ldg(wts + pix);
+  const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
+  const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
+  const int o_nw = t.y0 * w + t.x0;
+  for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+    const int c = __ldg(arg + b * (int64_t)P + pix);
+    if ((unsigned)c >= (unsigned)C) continue;          // never produced by the forward; guards foreign input
+    const float g = __ldg(gsal + b * (int64_t)P + pix);
+    float* dst = gcube + ((b * 6 + t.face) * C + c) * (int64_t)ww + o_nw;
+    if (xw_ok && yn_ok) atomicAdd(dst, g * wt.x);
+    if (xe_ok && yn_ok) atomicAdd(dst + 1, g * wt.y);
+    if (xw_ok && ys_ok) atomicAdd(dst + w, g * wt.z);
+    if (xe_ok && ys_ok) atomicAdd(dst + w + 1, g * wt.w);
   }
 }
 
@@ -358,7 +414,7 @@ static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts,
     CP360_LAUNCHED();
     return CP360_OK;
   }
-  int chb = MODE == 0 ? 8 : 32;
+  int chb = MODE == 0 ? 8 : 32;   // MODE 1 / 2: fewer atomics per pixel
   chb = (int)std::min<int64_t>(chb, C);
   dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)((C + chb - 1) / chb),
             (unsigned)std::min<int64_t>(B, 65535));
@@ -392,6 +448,40 @@ int cp360_c2e_max_fwd(const float* cube, const uint32_t* taps, const float* wts,
   launch_kernel(fill_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st, sal, n, -INFINITY);
   CP360_LAUNCHED();
   return launch_c2e<1>(cube, taps, wts, sal, B, C, w, st);
+}
+
+int cp360_c2e_max_arg_fwd(const float* cube, const uint32_t* taps, const float* wts, float* sal,
+                          int32_t* argmax, uint64_t* scratch, int64_t B, int64_t C, int w, void* stream) {
+  int rc = check_common(cube, taps, wts, sal, B, C, w);
+  if (rc != CP360_OK || B == 0) return rc;
+  CP360_CHECK_ARG(C > 0, CP360_ERR_BAD_ARG, "channel max over zero channels");
+  CP360_CHECK_ARG(argmax && scratch, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG(((uintptr_t)scratch % 8) == 0 && ((uintptr_t)argmax % 4) == 0, CP360_ERR_ALIGN,
+                  "scratch must be 8 B aligned, argmax 4 B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = B * 8 * (int64_t)w * w;
+  CP360_CUDA_OK(cudaMemsetAsync(scratch, 0, (size_t)n * sizeof(uint64_t), st));   // below every key
+  rc = launch_c2e<2>(cube, taps, wts, reinterpret_cast<float*>(scratch), B, C, w, st);
+  if (rc != CP360_OK) return rc;
+  launch_kernel(c2e_argmax_decode_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st,
+                reinterpret_cast<const unsigned long long*>(scratch), sal, argmax, n);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
+int cp360_c2e_max_bwd(const float* gsal, const int32_t* argmax, const uint32_t* taps, const float* wts,
+                      float* gcube, int64_t B, int64_t C, int w, void* stream) {
+  int rc = check_common(gsal, taps, wts, gcube, B, C, w);
+  if (rc != CP360_OK || B == 0 || C == 0) return rc;
+  CP360_CHECK_ARG(argmax && ((uintptr_t)argmax % 4) == 0, CP360_ERR_BAD_ARG, "argmax null or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = 8 * w * w;
+  CP360_CUDA_OK(cudaMemsetAsync(gcube, 0, (size_t)B * 6 * C * w * w * sizeof(float), st));
+  dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)std::min<int64_t>(B, 65535));
+  c2e_max_bwd_kernel<<<grid, kC2eThreads, 0, st>>>(gsal, argmax, taps, reinterpret_cast<const float4*>(wts),
+                                                   gcube, B, (int)C, w);
+  CP360_LAUNCHED();
+  return CP360_OK;
 }
 
 int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, int64_t B, int64_t C,

@@ -30,6 +30,7 @@
 #include "tma.cuh"
 #include "cubepad_row.cuh"
 #include "cubepad_cube.cuh"
+#include "cubepad_bwd.cuh"
 
 namespace cp360 {
 
@@ -563,6 +564,68 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   return CP360_OK;
 }
 
+// Tiling of the backward cube-tile kernel (cubepad_bwd.cuh): the padded gradient of all six faces of
+// kmax channels of one cube per stage. Returns false if it does not apply (the two-kernel path runs).
+static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const void* gy, const void* gx,
+                          CubeBwdArgs* a, size_t* smem_out) {
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  if (HoWo > 8191 || n_faces <= 0 || ((uintptr_t)gy % 16) != 0 || ((uintptr_t)gx % 4) != 0) return false;
+  int kq = 1;
+  while (kq <= 4 && (kq * HoWo) % 4) kq <<= 1;                 // 16 B granularity of the bulk copies
+  if (kq > 4 || C % kq) return false;
+  // measured on [96,256,32,32]: 48 KB x 3 stages (1 channel per stage) 162 us, 96 KB x 2 (2 channels) 115 us;
+  // on the 7x7 / 8x8 ConvLSTM sites 48 KB x 3 is the fastest of the settings tried (profiles/README.md)
+  const bool deep = g.H > 16;
+  const int stage_kb = std::max(1, env_int("CP360_BWD_STAGE_KB", deep ? 96 : 48));
+  int kmax = (stage_kb * 1024) / (6 * HoWo * 4);
+  kmax = std::min(kmax, C);
+  kmax -= kmax % kq;
+  if (kmax < kq) kmax = kq;
+  {
+    int p2 = 1;
+    while (p2 * 2 <= kmax) p2 *= 2;
+    if (p2 % kq == 0) kmax = p2;
+  }
+  int stages = std::min(kCubeMaxStages, std::max(2, env_int("CP360_BWD_STAGES", deep ? 2 : 3)));
+  a->C = C; a->kmax = kmax; a->cblocks = (C + kmax - 1) / kmax;
+  a->n_chunks = (n_faces / 6) * a->cblocks;
+  a->work = nullptr;
+  a->stage_words = 6 * kmax * HoWo;
+  a->offs_off = 3 * kCubeMaxStages * 8;
+  a->ent_off = (a->offs_off + (6 * HW + 1) * 2 + 15) & ~15;
+  a->ring_off = (a->ent_off + 6 * HoWo * 4 + 127) & ~127;
+  size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
+  while (smem > 220 * 1024 && stages > 2) {
+    --stages;
+    smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
+  }
+  if (smem > 220 * 1024) return false;
+  a->stages = stages;
+  *smem_out = smem;
+  return true;
+}
+
+static int launch_cube_bwd(CubeBwdArgs a, size_t smem, const CubePadGeom& g, cudaStream_t st) {
+  smem = exclusive_smem(smem, 1);
+  void (*kern)(const CubeBwdArgs, const CubePadGeom) = nullptr;
+  switch (a.kmax) {
+    case 1: kern = cubepad_bwd_cube_kernel<1>; break;
+    case 2: kern = cubepad_bwd_cube_kernel<2>; break;
+    case 4: kern = cubepad_bwd_cube_kernel<4>; break;
+    case 8: kern = cubepad_bwd_cube_kernel<8>; break;
+    case 16: kern = cubepad_bwd_cube_kernel<16>; break;
+    case 32: kern = cubepad_bwd_cube_kernel<32>; break;
+    default: kern = cubepad_bwd_cube_kernel<0>; break;
+  }
+  CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int cons_warps = std::min(31, std::max(1, env_int("CP360_BWD_WARPS", 16)));
+  a.work = acquire_work_counter(st);
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count()));
+  launch_kernel(kern, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);
+  CP360_LAUNCHED();
+  return CP360_OK;
+}
+
 static bool band_ok(const CubePadGeom& g) {
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
   return HW % 4 == 0 && HoWo % 4 == 0 && g.Wo <= kBandThreads;
@@ -1062,6 +1125,16 @@ int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C
   const int64_t total = n_planes * HW, total_b = n_planes * nb;
   const bool big = total >= 0x7fffffff || n_planes * (int64_t)(g.Ho * g.Wo) >= 0x7fffffff;
   const FastDiv d_HW = make_fastdiv((uint32_t)HW), d_W = make_fastdiv((uint32_t)g.W);
+  // small planes: one pass over the staged padded gradient (CP360_BWD_ALGO: 0 auto, 1 two kernels, 2 cube-tile)
+  const int bwd_algo = env_int("CP360_BWD_ALGO", 0);
+  if (bwd_algo != 1 && (g.H <= env_int("CP360_BWD_CUBE_MAX_H", 32) || bwd_algo == 2)) {
+    CubeBwdArgs ca; size_t smem;
+    if (cube_bwd_plan(g, n_faces, (int)C, gy, gx, &ca, &smem)) {
+      ca.gy = gy; ca.gx = gx;
+      return launch_cube_bwd(ca, smem, g, st);
+    }
+    CP360_CHECK_ARG(bwd_algo != 2, CP360_ERR_SHAPE, "backward cube-tile kernel does not apply to H=%d C=%d", g.H, (int)C);
+  }
   if (nb < HW) {
     const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
     if (big) cubepad_bwd_inner_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);

@@ -1,0 +1,205 @@
+// CubePad backward, cube-tile kernel (fp32, small planes) — included by cubepad.cu.
+//
+// The training path (temporal_model/train_temporal.py:105-107,167-170) back-propagates through every
+// CubePad of the ConvLSTM cell (model/clstm.py:57-64: [6N,2000,7,7], [6N,4000,7,7] x2 per step).
+// gx[f,y,x] = gy at the pixel's interior copy + gy at every halo position that copied the pixel
+// (the transpose of the forward gather). As in the forward cube-tile kernel the unit of work is all
+// six faces of a run of channels of one cube — the set inside which CubePad is closed — but here the
+// PADDED gradient is what is staged: six TMA bulk loads (one contiguous k*Ho*Wo chunk per face) per
+// tile, `stages` tiles ahead, every gy element read from DRAM exactly once, no atomics.
+//
+// A CSR table in shared memory, built once per CTA from cubepad_geom.h (cubepad_for_each_copy: the
+// push table inverted), lists for each input position (face, y, x) the staged words that hold its
+// copies: the interior copy first, then the halo copies in the fixed (entry, u, v) order — the same
+// order as cubepad_bwd_band_kernel, so both paths produce bit-identical, reproducible sums. A consumer
+// thread owns fixed input positions and walks the channels: LDS (+ adds for edge pixels) -> STG,
+// consecutive lanes on consecutive words of the gx plane.
+#pragma once
+#include "common.cuh"
+#include "cubepad_cube.cuh"
+#include "cubepad_geom.h"
+#include "tma.cuh"
+
+namespace cp360 {
+
+struct CubeBwdArgs {
+  const float* gy;
+  float* gx;
+  uint32_t* work;       // {next chunk, finished CTAs} (zero at launch) or nullptr: chunks dealt round-robin
+  int64_t n_chunks;     // N * cblocks
+  int32_t C;
+  int32_t kmax;         // channels per chunk (multiple of the bulk-copy channel quantum)
+  int32_t cblocks;
+  int32_t stages;
+  int32_t stage_words;  // 6 * kmax * Ho * Wo
+  int32_t offs_off;     // byte offset of the CSR row offsets (uint16 [6*H*W + 1])
+  int32_t ent_off;      // byte offset of the CSR entries (uint32 [6*Ho*Wo], staged word of channel 0)
+  int32_t ring_off;     // byte offset of the staging ring
+};
+
+// TK > 0: kmax known at compile time (the channel walk of a full chunk is unrolled in batches of 8)
+template <int TK>
+__global__ void __launch_bounds__(1024)
+cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [stages]
+  uint64_t* empty = full + kCubeMaxStages;                                // [stages]
+  int64_t* chunk_of = reinterpret_cast<int64_t*>(empty + kCubeMaxStages); // [stages] chunk id staged there, -1: end
+  uint16_t* offs = reinterpret_cast<uint16_t*>(smem_raw + a.offs_off);
+  uint32_t* ent = reinterpret_cast<uint32_t*>(smem_raw + a.ent_off);
+  const float* ring = reinterpret_cast<const float*>(smem_raw + a.ring_off);
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  const int n_in = 6 * HW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_cons = (int)blockDim.x - 32, n_cons_warps = n_cons >> 5;
+  const int kmax = TK ? TK : a.kmax;
+  const int fstride = kmax * HoWo;                                        // face stride in a stage
+
+  pdl_trigger();
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], n_cons_warps);
+    }
+    tma::fence_mbar_init();
+  }
+  // ---- CSR of the transposed map. Pass 1: copies per input position (interior copy included)
+  for (int e = tid; e < n_in; e += blockDim.x) {
+    const int f = e / HW, r = e - f * HW;
+    const int y = r / g.W, x = r - y * g.W;
+    int cnt = 1;
+    cubepad_for_each_copy(g, f, y, x, [&](int, int, int) { ++cnt; });
+    offs[e + 1] = (uint16_t)cnt;
+  }
+  __syncthreads();
+  if (warp == 0) {                                     // exclusive scan, one contiguous segment per lane
+    const int seg = (n_in + 31) / 32;
+    const int b = min(lane * seg, n_in), e1 = min(b + seg, n_in);
+    int sum = 0;
+    for (int i = b; i < e1; ++i) sum += offs[i + 1];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    int run = incl - sum;
+    for (int i = b; i < e1; ++i) {
+      const int c = offs[i + 1];
+      run += c;
+      offs[i + 1] = (uint16_t)run;                     // total = 6*Ho*Wo <= 49146 fits
+    }
+    if (lane == 0) offs[0] = 0;
+  }
+  __syncthreads();
+  // Pass 2: the entries — staged word (channel 0 of the chunk) of every copy
+  for (int e = tid; e < n_in; e += blockDim.x) {
+    const int f = e / HW, r = e - f * HW;
+    const int y = r / g.W, x = r - y * g.W;
+    int o = offs[e];
+    ent[o++] = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
+    cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
+      ent[o++] = (uint32_t)(dface * fstride + oy * g.Wo + ox);
+    });
+  }
+  __syncthreads();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ---------------- producer: draw chunks, stage them `stages` deep
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t ticket = a.work ? atomicAdd(a.work, 1u) : 0u;   // drawn one step ahead of its use
+      for (int64_t it = 0;; ++it) {
+        if (it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
+        int64_t q = (int64_t)blockIdx.x + it * gridDim.x;
+        if (a.work) {
+          q = (int64_t)ticket;
+          if (q < a.n_chunks) ticket = atomicAdd(a.work, 1u);
+        }
+        if (q >= a.n_chunks) {
+          chunk_of[s] = -1;
+          tma::mbar_arrive(&full[s]);                  // completes the phase: consumers see the end mark
+          break;
+        }
+        chunk_of[s] = q;
+        const int64_t n = q / a.cblocks;
+        const int c0 = (int)(q - n * a.cblocks) * kmax;
+        const int kl = min(kmax, a.C - c0);
+        const uint32_t bytes = (uint32_t)(kl * HoWo) * 4u;
+        tma::mbar_expect_tx(&full[s], 6u * bytes);
+        float* dst = const_cast<float*>(ring) + (size_t)s * a.stage_words;
+        const float* src = a.gy + ((n * 6) * a.C + c0) * HoWo;
+#pragma unroll
+        for (int f = 0; f < 6; ++f)
+          tma::bulk_load(dst + f * fstride, src + (int64_t)f * a.C * HoWo, bytes, &full[s]);
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
+      }
+      if (a.work && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {   // last CTA: hand the pair back zeroed
+        a.work[0] = 0;
+        a.work[1] = 0;
+        __threadfence();
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  const int ctid = tid - 32;
+  const int64_t CHW = (int64_t)a.C * HW;
+  int s = 0;
+  uint32_t ph = 0;
+  while (true) {
+    tma::mbar_wait(&full[s], ph);
+    const int64_t q = chunk_of[s];
+    if (q < 0) break;
+    const int64_t n = q / a.cblocks;
+    const int c0 = (int)(q - n * a.cblocks) * kmax;
+    const int kl = min(kmax, a.C - c0);
+    const float* in_s = ring + (size_t)s * a.stage_words;
+    float* __restrict__ out = a.gx + ((n * 6) * a.C + c0) * HW;
+    if (TK > 0 && kl == TK) {
+      constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
+#pragma unroll 1
+      for (int e = ctid; e < n_in; e += n_cons) {
+        const int o0 = offs[e], o1 = offs[e + 1];
+        const int f = e / HW, r = e - f * HW;
+        float* __restrict__ dp = out + f * CHW + r;
+        const float* sp0 = in_s + ent[o0];
+#pragma unroll
+        for (int c8 = 0; c8 < TK; c8 += KB) {
+          float acc[KB];
+#pragma unroll
+          for (int j = 0; j < KB; ++j) acc[j] = sp0[(c8 + j) * HoWo];
+#pragma unroll 1
+          for (int o = o0 + 1; o < o1; ++o) {
+            const float* sp = in_s + ent[o] + c8 * HoWo;
+#pragma unroll
+            for (int j = 0; j < KB; ++j) acc[j] += sp[j * HoWo];
+          }
+#pragma unroll
+          for (int j = 0; j < KB; ++j) __stcs(dp + (c8 + j) * HW, acc[j]);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int e = ctid; e < n_in; e += n_cons) {
+        const int o0 = offs[e], o1 = offs[e + 1];
+        const int f = e / HW, r = e - f * HW;
+        float* __restrict__ dp = out + f * CHW + r;
+#pragma unroll 1
+        for (int cc = 0; cc < kl; ++cc) {
+          float acc = in_s[ent[o0] + cc * HoWo];
+          for (int o = o0 + 1; o < o1; ++o) acc += in_s[ent[o] + cc * HoWo];
+          __stcs(dp + cc * HW, acc);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(&empty[s]);
+    if (++s == a.stages) { s = 0; ph ^= 1u; }
+  }
+}
+
+}  // namespace cp360

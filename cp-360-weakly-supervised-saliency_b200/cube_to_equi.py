@@ -85,12 +85,43 @@ class Cube2Equi:
 
     def to_equi_max(self, input_data, out=None):
         """Fused back-projection + channel max: [6B,C,w,w] -> [B,2w,4w]
-        (== torch.max(to_equi_nn(x), 1)[0], test_temporal.py:82-84)."""
+        (== torch.max(to_equi_nn(x), 1)[0], test_temporal.py:82-84). Differentiable: when the
+        input requires grad the arg-max channel is recorded and the backward scatters the map's
+        gradient to that channel's four taps (train_temporal.py:105-107)."""
         x = self._prepare(input_data)
+        if x.requires_grad and torch.is_grad_enabled():
+            y = _C2EMaxFn.apply(x, self)
+            return y if out is None else out.copy_(y)
         b, c, w = x.shape[0] // 6, x.shape[1], self.input_w
         if out is None:
             out = torch.empty((b, 2 * w, 4 * w), dtype=torch.float32, device=x.device)
         return self._launch("cp360_c2e_max_fwd", x, out, b, c)
+
+    def to_equi_max_with_indices(self, input_data):
+        """(sal [B,2w,4w] float32, argmax [B,2w,4w] int32) == torch.max(to_equi_nn(x), 1)."""
+        x = self._prepare(input_data)
+        b, c, w = x.shape[0] // 6, x.shape[1], self.input_w
+        sal = torch.empty((b, 2 * w, 4 * w), dtype=torch.float32, device=x.device)
+        arg = torch.empty((b, 2 * w, 4 * w), dtype=torch.int32, device=x.device)
+        scratch = torch.empty((b, 2 * w, 4 * w), dtype=torch.int64, device=x.device)
+        taps, wts = self._plan_on(x.device)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().cp360_c2e_max_arg_fwd(
+                x.data_ptr(), taps.data_ptr(), wts.data_ptr(), sal.data_ptr(), arg.data_ptr(),
+                scratch.data_ptr(), b, c, w, st))
+        return sal, arg
+
+    def _max_backward(self, gsal, arg, c):
+        b, w = gsal.shape[0], self.input_w
+        g = gsal.float().contiguous()
+        gx = torch.empty((6 * b, c, w, w), dtype=torch.float32, device=g.device)
+        taps, wts = self._plan_on(g.device)
+        with torch.cuda.device(g.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().cp360_c2e_max_bwd(
+                g.data_ptr(), arg.data_ptr(), taps.data_ptr(), wts.data_ptr(), gx.data_ptr(), b, c, w, st))
+        return gx
 
     def _cubic_plan_on(self, device):
         key = ("cubic", device.type, device.index)
@@ -131,3 +162,18 @@ class _C2EFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         return ctx.op._backward(gout), None
+
+
+class _C2EMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, op):
+        sal, arg = op.to_equi_max_with_indices(x.detach())
+        ctx.op, ctx.channels = op, x.shape[1]
+        ctx.save_for_backward(arg)
+        ctx.mark_non_differentiable(arg)
+        return sal
+
+    @staticmethod
+    def backward(ctx, gsal):
+        (arg,) = ctx.saved_tensors
+        return ctx.op._max_backward(gsal, arg, ctx.channels), None

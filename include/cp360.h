@@ -200,6 +200,20 @@ CP360_API int cp360_c2e_fwd(const float* cube_dev, const uint32_t* tap_dev, cons
 CP360_API int cp360_c2e_max_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
                       float* sal_dev, int64_t B, int64_t C, int w, void* stream);
 
+/* Device, fp32: the same channel max together with the channel it came from — the differentiable
+ * form the training path needs (train_temporal.py:105-107 backprops through to_equi_nn + torch.max):
+ * sal[B,2w,4w], argmax[B,2w,4w] int32 (lowest channel among equal maxima, as torch.max(dim)).
+ * scratch: caller-owned uint64[B*2w*4w] work buffer (overwritten). */
+CP360_API int cp360_c2e_max_arg_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
+                          float* sal_dev, int32_t* argmax_dev, uint64_t* scratch_dev, int64_t B, int64_t C,
+                          int w, void* stream);
+
+/* Device, fp32: backward of the fused channel max: gcube[6B,C,w,w] (zero-filled here) receives
+ * gsal[b,pix] * weight at the four taps of channel argmax[b,pix] — what autograd yields for
+ * torch.max(to_equi_nn(x), 1)[0] without materialising the [B,C,2w,4w] map or its gradient. */
+CP360_API int cp360_c2e_max_bwd(const float* gsal_dev, const int32_t* argmax_dev, const uint32_t* tap_dev,
+                      const float* wts_dev, float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
+
 /* Host: sampling plan of Cube2Equi.to_equi_cv2, cube_to_equi.py:68-91 — cv2.remap(INTER_CUBIC) fed
  * float32(out_coord) as it is (face pixels, no normalisation): s = cvRound(float32(coord)*32),
  *   tap_host[2w*4w] uint32: face<<28 | (sy&31)<<23 | (sx&31)<<18 | (sy>>5)<<9 | (sx>>5)

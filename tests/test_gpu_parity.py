@@ -272,6 +272,36 @@ def test_cubepad_backward_matches_autograd(dev):
         np.testing.assert_array_equal(ones.cpu().numpy().reshape(shape[0] // 6, 6, shape[1], shape[2], shape[3]), want)
 
 
+@pytest.mark.parametrize("shape,pad", [((12, 2000, 7, 7), 1), ((6, 4000, 7, 7), 1), ((12, 2048, 8, 8), 1), ((6, 64, 16, 16), 1),
+                                       ((6, 16, 32, 32), 1), ((12, 8, 14, 14), 3), ((6, 8, 9, 9), [4, 2, 3, 5]),
+                                       ((6, 4, 12, 12), [1, 2, 3, 0]), ((6, 7, 8, 8), 2), ((6, 3, 7, 7), 1),
+                                       ((6, 20, 5, 5), 5)])
+def test_cubepad_backward_cube_tile_equals_two_kernel_path(dev, shape, pad, monkeypatch):
+    """The cube-tile backward (staged padded gradient, CSR of the transposed map) and the two-kernel
+    path sum every pixel's copies in the same fixed order: bit-identical gradients."""
+    pads = cp360_b200.get_pad_size(pad)
+    gy = torch.randn(shape[0], shape[1], shape[2] + pads[2] + pads[3], shape[3] + pads[0] + pads[1], device=dev)
+    monkeypatch.setenv("CP360_BWD_ALGO", "1")
+    two = cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:])
+    monkeypatch.setenv("CP360_BWD_ALGO", "2")
+    try:
+        cube = cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:])
+    except _lib.CP360Error as e:
+        # only shapes whose channel count misses the 16 B quantum of the bulk copies may be refused
+        assert (shape[1] * (gy.shape[2] * gy.shape[3])) % 4 != 0 or shape[1] % 4 != 0, str(e)
+        pytest.skip("cube-tile backward does not apply: %s" % e)
+    monkeypatch.delenv("CP360_BWD_ALGO")
+    auto = cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:])
+    assert torch.equal(two, cube) and torch.equal(auto, two)
+    # against the transpose computed by torch (index_add over the forward map)
+    imap = torch.from_numpy(ocp.index_map(shape[2], shape[3], pad).reshape(-1).astype(np.int64)).to(dev)
+    n6, C, H, W = shape
+    g = gy.reshape(n6 // 6, 6, C, -1).permute(0, 2, 1, 3).reshape(n6 // 6, C, -1).double()
+    want = torch.zeros(n6 // 6, C, 6 * H * W, device=dev, dtype=torch.float64).index_add_(2, imap, g)
+    want = want.reshape(n6 // 6, C, 6, H, W).permute(0, 2, 1, 3, 4).reshape(n6, C, H, W)
+    torch.testing.assert_close(cube.double(), want, rtol=0, atol=1e-5)
+
+
 def test_cubepad_is_stream_ordered(dev):
     s = torch.cuda.Stream(device=dev)
     x = torch.randn(6, 64, 32, 32, device=dev)
@@ -539,6 +569,46 @@ def test_c2e_backward_matches_autograd(dev):
             flat.index_add_(1, idx, contrib)
             want = flat.reshape(C, 6, w, w).permute(1, 0, 2, 3).contiguous()
         torch.testing.assert_close(x.grad.double(), want, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("w,C,B", [(7, 1000, 1), (8, 2048, 2), (8, 5, 3), (16, 64, 2), (20, 7, 2), (40, 3, 1)])
+def test_c2e_max_with_indices_and_backward(dev, w, C, B):
+    """Differentiable fused c2e + channel max (train_temporal.py:105-107): value and arg-max channel equal
+    torch.max over the materialised map; the backward equals autograd through to_equi_nn + torch.max."""
+    c2e = cp360_b200.Cube2Equi(w)
+    x = torch.randn(6 * B, C, w, w, device=dev)
+    full = c2e.to_equi_nn(x)
+    want_v, want_i = full.max(1)
+    sal, arg = c2e.to_equi_max_with_indices(x)
+    assert arg.dtype == torch.int32 and tuple(arg.shape) == (B, 2 * w, 4 * w)
+    assert torch.equal(sal, want_v)
+    assert torch.equal(arg.long(), want_i)
+    assert torch.equal(sal, c2e.to_equi_max(x))
+    # backward: fused path vs autograd over the un-fused ops
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    g = torch.randn(B, 2 * w, 4 * w, device=dev)
+    ya = c2e.to_equi_max(xa)
+    assert ya.requires_grad and torch.equal(ya.detach(), want_v)
+    ya.backward(g)
+    c2e.to_equi_nn(xb).max(1)[0].backward(g)
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=0, atol=1e-5)
+    assert int((xa.grad != 0).sum().item()) <= 4 * B * 8 * w * w
+
+
+def test_c2e_max_ties_pick_lowest_channel(dev):
+    """Equal maxima: the lowest channel wins, as torch.max(dim) documents (first maximal index)."""
+    c2e = cp360_b200.Cube2Equi(8)
+    base = torch.randn(6, 1, 8, 8, device=dev)
+    x = base.repeat(1, 40, 1, 1).contiguous()            # 40 identical channels
+    x[:, 7] += 1.0                                        # channel 7 and its copy 23 are the maxima
+    x[:, 23] = x[:, 7]
+    sal, arg = c2e.to_equi_max_with_indices(x)
+    full = c2e.to_equi_nn(x)
+    assert torch.equal(sal, full.max(1)[0])
+    pos = (full[:, 7] > full[:, 0])                       # pixels whose taps are not all zero-weighted
+    assert torch.equal(arg[pos], torch.full_like(arg[pos], 7))
+    assert int(arg.min().item()) >= 0 and int(arg.max().item()) < 40
 
 
 def test_c2e_full_size_properties(dev):

@@ -73,6 +73,12 @@ def main():
             n = 6 * B if (C, H) != (64, 256) else 12
             x = torch.randn(n, C, H, H, device=dev)
             nbytes = n * C * (H * H + (H + 2 * p) ** 2) * 4
+            # the practical ceiling at this size: a plain device copy moving the same number of bytes
+            ca = torch.empty(nbytes // 8, dtype=torch.float32, device=dev)
+            cb = torch.empty_like(ca)
+            report("  d2d copy of the same bytes [%d,%d,%d,%d] p%d" % (n, C, H, H, p), nbytes,
+                   timeit(lambda: cb.copy_(ca), args.iters, flush))
+            del ca, cb
             for algo, an in ((1, "generic"), (4, "cube"), (5, "row"), (6, "cube2")):
                 try:
                     cp360_b200.cubepad_forward(x, (p, p, p, p), algo=algo)
@@ -153,7 +159,7 @@ def main():
                    timeit(lambda: c2e.to_equi_cv2(x), args.iters, flush))
     if args.only in ("", "bwd"):
         # row f1: the training path's backward kernels (train_temporal.py:105-107,167-170)
-        for C, H, p in ((64, 128, 1), (256, 32, 1), (2048, 8, 1), (2000, 7, 1), (4000, 7, 1)):
+        for C, H, p in ((64, 128, 1), (128, 64, 1), (256, 32, 1), (512, 16, 1), (2048, 8, 1), (2000, 7, 1), (4000, 7, 1)):
             n = 6 * B
             gy = torch.randn(n, C, H + 2 * p, H + 2 * p, device=dev)
             nbytes = n * C * (H * H + (H + 2 * p) ** 2) * 4
@@ -165,6 +171,21 @@ def main():
             g = torch.randn(B, C, 2 * w, 4 * w, device=dev)
             report("c2e bwd  [%d,%d,%d,%d]" % (B, C, 2 * w, 4 * w), B * C * 14 * w * w * 4,
                    timeit(lambda: c2e._backward(g), args.iters, flush))
+            # training head (train_temporal.py:105-107): map + channel max, forward and backward
+            x = torch.randn(6 * B, C, w, w, device=dev, requires_grad=True)
+            gs = torch.randn(B, 2 * w, 4 * w, device=dev)
+
+            def unfused():
+                x.grad = None
+                c2e.to_equi_nn(x).max(1)[0].backward(gs)
+
+            def fused():
+                x.grad = None
+                c2e.to_equi_max(x).backward(gs)
+            report("c2e+max fwd+bwd [%d,%d,%d,%d] to_equi_nn + torch.max + autograd" % (6 * B, C, w, w),
+                   2 * B * C * 6 * w * w * 4, timeit(unfused, args.iters, flush))
+            report("c2e+max fwd+bwd [%d,%d,%d,%d] fused (max_arg_fwd + max_bwd)" % (6 * B, C, w, w),
+                   2 * B * C * 6 * w * w * 4, timeit(fused, args.iters, flush))
     if args.json:
         with open(args.json, "w") as f:
             json.dump(rows, f, indent=1)
