@@ -40,7 +40,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=16, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=32,
+                    help="frames per step per GPU (measured: 16 -> 23.4k, 32 -> 25.0k, 64 -> 25.5k frames/s; every "
+                         "launch pays a fixed ~5 us of ramp/tail inside the chain, profiles/README.md)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -336,14 +338,19 @@ def run_b200(args, rank, world, local_rank):
     prof_steps = min(K, 20)
     per_class = {}
     per_site = {}
-    for _ in range(prof_steps):
+    # prof_steps + 1 steps back to back, no host sync in between, the first one dropped: with the GPU idle
+    # at the start of a step the first interval would also contain the host's launch latency
+    recorded = []
+    for _ in range(prof_steps + 1):
         names.clear()
         marks.clear()
         pipe.step(frames, on_launch=hook)
-        torch.cuda.synchronize()
-        for i in range(len(marks) - 1):
-            name, site = names[i]
-            dt = marks[i].elapsed_time(marks[i + 1])
+        recorded.append((list(names), list(marks)))
+    torch.cuda.synchronize()
+    for step_names, step_marks in recorded[1:]:
+        for i in range(len(step_marks) - 1):
+            name, site = step_names[i]
+            dt = step_marks[i].elapsed_time(step_marks[i + 1])
             if name == "cubepad":
                 C, H, p = pipe.sites[site]
                 algo = lib.cp360_cubepad_pick_algo(6 * B, C, H, H, p, p, p, p, 4, 1)
@@ -362,6 +369,7 @@ def run_b200(args, rank, world, local_rank):
             c["ms"] += dt
             c["bytes"] += nbytes
             c["launches"] += 1
+    del recorded
     tot_ms = sum(c["ms"] for c in per_class.values())
     peak, peak_src = measured_peak_gbs()
     kernels = {}

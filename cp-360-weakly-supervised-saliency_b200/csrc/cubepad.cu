@@ -338,7 +338,10 @@ cubepad_cube_kernel(const CubeArgs a, const __grid_constant__ CubePadGeom g) {
 //   cubepad_bwd_band_kernel    a thread per band pixel: interior copy + the gradients of the halo
 //                              positions that copied it (cubepad_for_each_copy: the push table
 //                              inverted), summed in a fixed order -> bit-reproducible gradients
-// The two kernels write disjoint pixels. BIG: more than 2^31 elements (64-bit index arithmetic).
+// The scalar inner kernel and the band kernel write disjoint pixels; the vectorised inner kernel
+// (W % 4 == 0) writes every pixel's interior copy and the band kernel, which follows it on the
+// stream, overwrites the band pixels. Planes with H <= 32 take the one-pass cube-tile kernel of
+// cubepad_bwd.cuh instead. BIG: more than 2^31 elements (64-bit index arithmetic).
 // ------------------------------------------------------------------------------------------
 template <bool BIG>
 __global__ void __launch_bounds__(256)
@@ -353,6 +356,40 @@ cubepad_bwd_inner_kernel(const float* __restrict__ gy, float* __restrict__ gx, i
     const int y = fdiv(e, d_W), x = e - y * g.W;
     if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) >= pm)
       gx[i] = __ldcs(gy + plane * HoWo + (y + g.pt) * g.Wo + x + g.pl);
+  }
+}
+
+// W % 4 == 0 and a 16 B-aligned gx: the same copy four pixels per thread and two such quads in flight
+// (eight independent loads per thread — one 4 B load per thread and iteration is latency-bound at
+// ~2.4 TB/s), one 16 B store per quad. Writes EVERY pixel with its interior copy: the band kernel runs
+// after it on the stream and overwrites the band pixels with their full sums.
+template <bool BIG>
+__global__ void __launch_bounds__(256)
+cubepad_bwd_inner_vec_kernel(const float* __restrict__ gy, float4* __restrict__ gx4, int64_t total4,
+                             const __grid_constant__ CubePadGeom g, FastDiv d_HW4, FastDiv d_W4) {
+  const int HoWo = g.Ho * g.Wo, HW4 = (g.H * g.W) >> 2, W4 = g.W >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += 2 * stride) {
+    float v[2][4];
+    bool ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int64_t ik = i + k * stride;
+      ok[k] = ik < total4;
+      if (ok[k]) {
+        int64_t plane;
+        int e;
+        if (BIG) { plane = ik / HW4; e = (int)(ik - plane * HW4); }
+        else { const int p32 = fdiv((int)ik, d_HW4); plane = p32; e = (int)ik - p32 * HW4; }
+        const int y = fdiv(e, d_W4), x = (e - y * W4) << 2;
+        const float* src = gy + plane * HoWo + (y + g.pt) * g.Wo + x + g.pl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[k][j] = __ldcs(src + j);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (ok[k]) __stcs(gx4 + i + k * stride, make_float4(v[k][0], v[k][1], v[k][2], v[k][3]));
   }
 }
 
@@ -574,9 +611,9 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
   while (kq <= 4 && (kq * HoWo) % 4) kq <<= 1;                 // 16 B granularity of the bulk copies
   if (kq > 4 || C % kq) return false;
   // measured on [96,256,32,32]: 48 KB x 3 stages (1 channel per stage) 162 us, 96 KB x 2 (2 channels) 115 us;
-  // on the 7x7 / 8x8 ConvLSTM sites 48 KB x 3 is the fastest of the settings tried (profiles/README.md)
+  // on the 7x7 / 8x8 / 16x16 sites 64 KB x 3 is the fastest of the settings tried (profiles/README.md)
   const bool deep = g.H > 16;
-  const int stage_kb = std::max(1, env_int("CP360_BWD_STAGE_KB", deep ? 96 : 48));
+  const int stage_kb = std::max(1, env_int("CP360_BWD_STAGE_KB", deep ? 96 : 64));
   int kmax = (stage_kb * 1024) / (6 * HoWo * 4);
   kmax = std::min(kmax, C);
   kmax -= kmax % kq;
@@ -593,7 +630,8 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
   a->stage_words = 6 * kmax * HoWo;
   a->offs_off = 3 * kCubeMaxStages * 8;
   a->ent_off = (a->offs_off + (6 * HW + 1) * 2 + 15) & ~15;
-  a->ring_off = (a->ent_off + 6 * HoWo * 4 + 127) & ~127;
+  a->pos_off = (a->ent_off + 6 * HoWo * 4 + 15) & ~15;
+  a->ring_off = (a->pos_off + 6 * HW * 8 + 127) & ~127;
   size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
   while (smem > 220 * 1024 && stages > 2) {
     --stages;
@@ -1136,13 +1174,21 @@ int cp360_cubepad_bwd_f32(const float* gy, float* gx, int64_t n_faces, int64_t C
     CP360_CHECK_ARG(bwd_algo != 2, CP360_ERR_SHAPE, "backward cube-tile kernel does not apply to H=%d C=%d", g.H, (int)C);
   }
   if (nb < HW) {
-    const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-    if (big) cubepad_bwd_inner_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);
-    else cubepad_bwd_inner_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);
+    if (g.W % 4 == 0 && ((uintptr_t)gx % 16) == 0 && env_int("CP360_BWD_INNER_VEC", 1)) {
+      const int64_t total4 = total / 4;
+      const int64_t blocks = std::min<int64_t>((total4 + 511) / 512, (int64_t)sm_count() * 8);
+      const FastDiv d_HW4 = make_fastdiv((uint32_t)(HW / 4)), d_W4 = make_fastdiv((uint32_t)(g.W / 4));
+      if (big) cubepad_bwd_inner_vec_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, reinterpret_cast<float4*>(gx), total4, g, d_HW4, d_W4);
+      else cubepad_bwd_inner_vec_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(gy, reinterpret_cast<float4*>(gx), total4, g, d_HW4, d_W4);
+    } else {
+      const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+      if (big) cubepad_bwd_inner_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);
+      else cubepad_bwd_inner_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total, g, pm, d_HW, d_W);
+    }
     CP360_LAUNCHED();
   }
   if (nb > 0) {
-    const int64_t blocks = std::min<int64_t>((total_b + 255) / 256, (int64_t)sm_count() * 16);
+    const int64_t blocks = std::min<int64_t>((total_b + 255) / 256, (int64_t)sm_count() * 64);   // short threads: more waves hide the gathers
     const FastDiv d_nb = make_fastdiv((uint32_t)nb), d_2pm = make_fastdiv((uint32_t)std::max(1, 2 * pm)),
                   d_C = make_fastdiv((uint32_t)C);
     if (big) cubepad_bwd_band_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(gy, gx, total_b, (int)C, g, pm, nb, d_nb, d_W, d_2pm, d_C);

@@ -34,6 +34,7 @@ struct CubeBwdArgs {
   int32_t stage_words;  // 6 * kmax * Ho * Wo
   int32_t offs_off;     // byte offset of the CSR row offsets (uint16 [6*H*W + 1])
   int32_t ent_off;      // byte offset of the CSR entries (uint32 [6*Ho*Wo], staged word of channel 0)
+  int32_t pos_off;      // byte offset of the per-position records (uint2 [6*H*W])
   int32_t ring_off;     // byte offset of the staging ring
 };
 
@@ -47,6 +48,8 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   int64_t* chunk_of = reinterpret_cast<int64_t*>(empty + kCubeMaxStages); // [stages] chunk id staged there, -1: end
   uint16_t* offs = reinterpret_cast<uint16_t*>(smem_raw + a.offs_off);
   uint32_t* ent = reinterpret_cast<uint32_t*>(smem_raw + a.ent_off);
+  // per input position: .x = staged word of its interior copy, .y = face << 29 | halo copies << 16 | pixel
+  uint2* pos = reinterpret_cast<uint2*>(smem_raw + a.pos_off);
   const float* ring = reinterpret_cast<const float*>(smem_raw + a.ring_off);
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
   const int n_in = 6 * HW;
@@ -96,11 +99,14 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   for (int e = tid; e < n_in; e += blockDim.x) {
     const int f = e / HW, r = e - f * HW;
     const int y = r / g.W, x = r - y * g.W;
-    int o = offs[e];
-    ent[o++] = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
+    const int o0 = offs[e];
+    int o = o0;
+    const uint32_t inner = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
+    ent[o++] = inner;
     cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
       ent[o++] = (uint32_t)(dface * fstride + oy * g.Wo + ox);
     });
+    pos[e] = make_uint2(inner, (uint32_t)f << 29 | (uint32_t)(o - o0 - 1) << 16 | (uint32_t)r);
   }
   __syncthreads();
   pdl_wait();
@@ -163,17 +169,18 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
       constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
 #pragma unroll 1
       for (int e = ctid; e < n_in; e += n_cons) {
-        const int o0 = offs[e], o1 = offs[e + 1];
-        const int f = e / HW, r = e - f * HW;
-        float* __restrict__ dp = out + f * CHW + r;
-        const float* sp0 = in_s + ent[o0];
+        const uint2 pe = pos[e];
+        const int n_halo = (int)((pe.y >> 16) & 0x1fffu);
+        float* __restrict__ dp = out + (int64_t)(pe.y >> 29) * CHW + (pe.y & 0xffffu);
+        const float* sp0 = in_s + pe.x;
+        const int o0 = n_halo ? (int)offs[e] : 0;
 #pragma unroll
         for (int c8 = 0; c8 < TK; c8 += KB) {
           float acc[KB];
 #pragma unroll
           for (int j = 0; j < KB; ++j) acc[j] = sp0[(c8 + j) * HoWo];
 #pragma unroll 1
-          for (int o = o0 + 1; o < o1; ++o) {
+          for (int o = o0 + 1; o <= o0 + n_halo; ++o) {
             const float* sp = in_s + ent[o] + c8 * HoWo;
 #pragma unroll
             for (int j = 0; j < KB; ++j) acc[j] += sp[j * HoWo];
@@ -185,13 +192,14 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     } else {
 #pragma unroll 1
       for (int e = ctid; e < n_in; e += n_cons) {
-        const int o0 = offs[e], o1 = offs[e + 1];
-        const int f = e / HW, r = e - f * HW;
-        float* __restrict__ dp = out + f * CHW + r;
+        const uint2 pe = pos[e];
+        const int n_halo = (int)((pe.y >> 16) & 0x1fffu);
+        float* __restrict__ dp = out + (int64_t)(pe.y >> 29) * CHW + (pe.y & 0xffffu);
+        const int o0 = n_halo ? (int)offs[e] : 0;
 #pragma unroll 1
         for (int cc = 0; cc < kl; ++cc) {
-          float acc = in_s[ent[o0] + cc * HoWo];
-          for (int o = o0 + 1; o < o1; ++o) acc += in_s[ent[o] + cc * HoWo];
+          float acc = in_s[pe.x + cc * HoWo];
+          for (int o = o0 + 1; o <= o0 + n_halo; ++o) acc += in_s[ent[o] + cc * HoWo];
           __stcs(dp + cc * HW, acc);
         }
       }
