@@ -395,7 +395,11 @@ def run_b200(args, rank, world, local_rank):
     if os.path.exists(traffic_path):
         try:
             with open(traffic_path) as f:
-                roofline["traffic"] = json.load(f).get(dom)
+                tj = json.load(f)
+            # ncu captures are per launch at a stated batch: only valid for a run at that batch
+            if int(tj.get("_frames_per_launch", 16)) == B:
+                roofline["traffic"] = tj.get(dom)
+                roofline["traffic_source"] = "profiles/traffic.json (ncu --set full, B=%d)" % B
         except Exception:
             pass
 

@@ -3,7 +3,7 @@
 summaries of every ncu --set full capture, the launch list, the bench line, and profiles/traffic.json
 (measured DRAM bytes per launch of each kernel class, read by bench.py for roofline.traffic).
 
-    python tools/make_profiles.py gpurun_out/c2 r01_v4
+    python tools/make_profiles.py gpurun_out/c2 r01_v4 [frames per launch of the captures, default 16]
 """
 import csv
 import json
@@ -36,7 +36,7 @@ def num(rec, units, key):
     return float(rec[key].replace(",", "")) * UNIT.get(units[key], 1.0)
 
 
-def main(src, tag):
+def main(src, tag, batch=16):
     prof = os.path.join(ROOT, "profiles")
     lines, classes = [], {}
     for fn in sorted(os.listdir(src)):
@@ -64,17 +64,19 @@ def main(src, tag):
     with open(os.path.join(prof, "%s_ncu_full.txt" % tag), "w") as f:
         f.write("\n".join(lines) + "\n")
     traffic = {k: int(v[0] / v[1]) for k, v in classes.items()}
+    traffic["_frames_per_launch"] = batch
     traffic["_note"] = ("DRAM bytes (read+write) per launch from ncu --set full, averaged over the launches of the class in "
-                        "one chain step at B=16; isolated captures leave part of the output dirty in the 126 MB L2 at kernel "
-                        "end, so writes are under-counted for sites whose output is < L2 (source: profiles/%s_ncu_full.txt)" % tag)
+                        "one chain step at B=%d; isolated captures leave part of the output dirty in the 126 MB L2 at kernel "
+                        "end, so writes are under-counted for sites whose output is < L2 (source: profiles/%s_ncu_full.txt)" % (batch, tag))
     with open(os.path.join(prof, "traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)
     for a, b in (("bench.json", "%s_bench.json"), ("bench.err", "%s_bench_sites.txt"), ("kbench.txt", "%s_kbench.txt"),
-                 ("launches.csv", "%s_launches.csv")):
+                 ("launches.csv", "%s_launches.csv"), ("bench_reference.json", "%s_bench_reference.json"),
+                 ("pytest_gpu.log", "%s_pytest_gpu.log"), ("smoke.log", "%s_smoke.log")):
         if os.path.exists(os.path.join(src, a)):
             shutil.copy(os.path.join(src, a), os.path.join(prof, b % tag))
     print(json.dumps(traffic, indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 16)
