@@ -145,7 +145,7 @@ def run_reference(args, rank):
                                        "Python and cannot travel to the GPU box)" % (done, S, dt)},
             "e2e": {"value": round(v, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -479,9 +479,29 @@ def run_b200(args, rank, world, local_rank):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K),
                 "roofline": roofline, "kernels": kernels, "tuning": tuning, "fused_first_site": fused_first,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: native libraries write there too (NCCL prints its version banner on
+    stdout at communicator creation), so fd 1 is pointed at stderr for the rest of the process and the line
+    goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -499,6 +519,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     run_b200(args, rank, world, local_rank)
 
 
