@@ -3,7 +3,7 @@
 summaries of every ncu --set full capture, the launch list, the bench line, and profiles/traffic.json
 (measured DRAM bytes per launch of each kernel class, read by bench.py for roofline.traffic).
 
-    python tools/make_profiles.py gpurun_out/c2 r01_v4 [frames per launch of the captures, default 16]
+    python tools/make_profiles.py gpurun_out/c2 r01_v4 [frames per launch of the captures, default 16] [output dir, default profiles/]
 """
 import csv
 import json
@@ -26,7 +26,12 @@ SITE_COUNT = {"3_256_3": 1, "64_128_1": 1, "64_64_1": 3, "128_64_1": 1, "128_32_
 
 
 def raw(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """Records of a report: from the .ncu-rep, or from `ncu -i x.ncu-rep --page raw --csv > x.raw.csv` made on the box
+    (reports with embedded cubins are too large to bring back in numbers)."""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     return [({h: r[i] for i, h in enumerate(hdr)}, {h: units[i] for i, h in enumerate(hdr)}) for r in rows[2:]]
@@ -36,15 +41,34 @@ def num(rec, units, key):
     return float(rec[key].replace(",", "")) * UNIT.get(units[key], 1.0)
 
 
-def main(src, tag, batch=16):
-    prof = os.path.join(ROOT, "profiles")
+def main(src, tag, batch=16, prof=None):
+    prof = prof or os.path.join(ROOT, "profiles")
     lines, classes = [], {}
-    for fn in sorted(os.listdir(src)):
-        if not fn.endswith(".ncu-rep"):
+    records = []                                   # (file, site, record, units)
+    have = set(os.listdir(src))
+    for fn in sorted(have):
+        if fn.endswith(".raw.csv"):
+            if fn.replace(".raw.csv", ".ncu-rep") in have:
+                continue
+        elif not fn.endswith(".ncu-rep"):
             continue
-        for rec, units in raw(os.path.join(src, fn)):
+        recs = raw(os.path.join(src, fn))
+        fn = fn.replace(".raw.csv", ".ncu-rep")
+        order = os.path.join(src, fn.replace(".ncu-rep", ".order"))
+        if os.path.exists(order):                  # tools/prof_all.py: one record per spec, in this order
+            sites = open(order).read().split()
+            assert len(sites) == len(recs), "%s: %d records for %d specs" % (fn, len(recs), len(sites))
+            records += [(fn, st.replace("cubepad_", ""), r, u) for st, (r, u) in zip(sites, recs)]
+        else:
+            records += [(fn, fn.replace("full_cubepad_", "").replace(".ncu-rep", ""), r, u) for r, u in recs]
+    seen = set()
+    for fn, site, rec, units in records:
+        if True:
             name = rec["Kernel Name"]
-            lines.append("### %s  ::  %s" % (fn, name[:90]))
+            if (site, name) in seen:               # the same site captured twice (e.g. once more with source import)
+                continue
+            seen.add((site, name))
+            lines.append("### %s [%s]  ::  %s" % (fn, site, name[:90]))
             for k in KEYS:
                 if k in rec:
                     lines.append("  %-62s %16s %s" % (k, rec[k], units[k]))
@@ -54,7 +78,6 @@ def main(src, tag, batch=16):
             dram = num(rec, units, "dram__bytes_read.sum") + num(rec, units, "dram__bytes_write.sum")
             us = num(rec, units, "gpu__time_duration.sum")
             lines.append("  => DRAM read+write %.1f MB in %.1f us = %.0f GB/s" % (dram / 1e6, us, dram / us / 1e3))
-            site = fn.replace("full_cubepad_", "").replace(".ncu-rep", "")
             cls = ("cubepad_row_kernel" if "row_kernel" in name else "cubepad_cube2_kernel" if "cube2" in name else
                    "e2c_kernel" if "e2c" in name else "c2e_small_kernel<max> (+fill)" if "c2e" in name else name)
             n = SITE_COUNT.get(site, 1)
@@ -79,4 +102,4 @@ def main(src, tag, batch=16):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 16)
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 16, sys.argv[4] if len(sys.argv) > 4 else None)
