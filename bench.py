@@ -442,6 +442,8 @@ def run_b200(args, rank, world, local_rank):
                 dt = float(t.item())
             return world * B * E / dt
 
+        # several GPUs on one host: pinned staging buffers on the GPU's own NUMA node (best effort, advisory)
+        numa = cp360_b200.prefer_gpu_numa_node(dev) if world > 1 else None
         host_u8 = [torch.randint(0, 256, (B, EQUI_H, EQUI_W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
         v_u8 = run_e2e(host_u8)
         del host_u8
@@ -454,6 +456,8 @@ def run_b200(args, rank, world, local_rank):
                "timing": "CUDA events on the compute stream around the whole call, max over ranks",
                "wall_clock_value": round(world * B * E / wall[0], 1),
                "f32_host_frames": {"value": round(v_f32, 1), "h2d_bytes_per_step": B * EQUI_H * EQUI_W * 3 * 4}}
+        if numa is not None:
+            e2e["host_numa_preference_rank0"] = numa
     sampler.stop()
     clocks = sampler.summary()
 

@@ -16,7 +16,8 @@ from .cam import SaliencyHead, cam_scores, cam_weight
 from .cube_to_equi import Cube2Equi
 from .equi_to_cube import Equi2Cube
 from .io import backproject_files, load_cube_feat, load_npy, npy_header, save_npy
-from .pipeline import SphericalPipeline, gather_maps, resnet50_cubepad_sites, shard_range
+from .pipeline import (SphericalPipeline, gather_maps, gpu_numa_node, prefer_gpu_numa_node,
+                       resnet50_cubepad_sites, shard_range)
 
 __all__ = ["CubePad", "CubePadding", "get_pad_size", "cubepad_forward", "cubepad_index_map", "cubepad_fused", "cubepad_cat", "cubepad_bn_relu",
            "Equi2Cube", "Cube2Equi", "SaliencyHead", "cam_scores", "cam_weight", "SphericalPipeline", "gather_maps", "resnet50_cubepad_sites",

@@ -60,6 +60,49 @@ def gather_maps(local_maps, n_total, group=None):
     return torch.cat([out[r * n_max:r * n_max + (b - a)] for r, (a, b) in enumerate(sizes)], 0)
 
 
+def gpu_numa_node(device):
+    """NUMA node the GPU's PCIe function hangs off (sysfs), or -1 when the platform does not say."""
+    props = torch.cuda.get_device_properties(device)
+    try:
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            return int(f.read().strip())
+    except (AttributeError, OSError, ValueError):
+        return -1
+
+
+def prefer_gpu_numa_node(device):
+    """Best effort, for multi-GPU hosts: make this process PREFER (MPOL_PREFERRED — falls back to other nodes,
+    never fails an allocation) host memory on the GPU's own NUMA node, so that pinned staging buffers allocated
+    afterwards (``process_host``'s host batches) are read by the GPU's copy engines without crossing the socket
+    interconnect. One process per GPU is the deployment model, so a process-wide policy is the
+    right grain. Returns a small dict saying what was done; never raises."""
+    import ctypes
+    import os
+    info = {"node": -1, "applied": False}
+    try:
+        node = gpu_numa_node(device)
+        info["node"] = node
+        if node < 0 or not os.path.isdir("/sys/devices/system/node/node%d" % node):
+            info["why"] = "GPU NUMA node unknown"
+            return info
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        SYS_set_mempolicy, MPOL_PREFERRED = 238, 1          # x86_64
+        if os.uname().machine != "x86_64":
+            info["why"] = "set_mempolicy syscall number only known for x86_64"
+            return info
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), 16 * 64)
+        if rc != 0:
+            info["why"] = "set_mempolicy: " + os.strerror(ctypes.get_errno())
+            return info
+        info["applied"] = True
+    except Exception as e:                                  # noqa: BLE001 - advisory only
+        info["why"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 class SphericalPipeline:
     def __init__(self, equi_h=960, equi_w=1920, cube=256, cam_channels=1000, feat_channels=2048,
                  device=None, seed=1234, fuse_first_site=False):

@@ -60,3 +60,20 @@ def test_shard_range_properties():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_prefer_gpu_numa_node_is_advisory(monkeypatch):
+    """The NUMA preference of the multi-GPU host path never raises: unknown node -> not applied;
+    a known node -> MPOL_PREFERRED (allocations keep working either way)."""
+    import importlib
+    import cp360_b200
+    pl = importlib.import_module(cp360_b200.SphericalPipeline.__module__)
+    monkeypatch.setattr(pl, "gpu_numa_node", lambda d: -1)
+    info = pl.prefer_gpu_numa_node(0)
+    assert info["applied"] is False and "why" in info
+    monkeypatch.setattr(pl, "gpu_numa_node", lambda d: 0)
+    info = pl.prefer_gpu_numa_node(0)
+    assert info["node"] == 0 and (info["applied"] or "why" in info)
+    assert torch.empty(1 << 16).fill_(1).sum().item() == float(1 << 16)
+    monkeypatch.setattr(pl, "gpu_numa_node", lambda d: 1000)          # no such node on this host
+    assert pl.prefer_gpu_numa_node(0)["applied"] is False
