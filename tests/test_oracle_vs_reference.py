@@ -1,0 +1,128 @@
+"""Live pin of the oracle AND of the C-ABI host builders against the UNMODIFIED reference, executed where it
+lies (/root/reference, build container only; skipped on the GPU box where it does not exist).
+
+The committed fixtures (tests/golden/) pin a fixed list of configurations; this file sweeps seeded random
+ones on top — shapes, asymmetric pads, resolutions and fields of view the fixtures do not hold — so the
+restatement cannot drift from the reference on a case nobody wrote down. Bars as everywhere: CubePad and the
+integer sampling maps bit-exact, e2c faces bit-exact (cv2 arithmetic), c2e within 4e-6 (CPU grid_sample)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import cp360_b200
+from cp360_b200 import _lib
+from oracle import c2e as oc2e
+from oracle import cubepad as ocp
+from oracle import e2c as oe2c
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import _ref_loader  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not _ref_loader.available(), reason="reference sources not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    warnings.filterwarnings("ignore")
+    return _ref_loader.load()
+
+
+def _random_pad_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n):
+        H = int(rng.integers(1, 19))
+        if rng.random() < 0.4:
+            pad = int(rng.integers(0, min(H, 5) + 1))
+        else:
+            pad = [int(v) for v in rng.integers(0, min(H, 5) + 1, size=4)]
+        cases.append((H, pad))
+    return cases
+
+
+@pytest.mark.parametrize("H,pad", _random_pad_cases(48, seed=360))
+def test_cubepad_index_map_live(ref, H, pad):
+    """model/cube_pad.py:23-216 on x = arange == oracle.index_map == cp360_cubepad_build_map (bit-exact)."""
+    cube_pad = ref[0]
+    x = torch.arange(6 * H * H, dtype=torch.float64).reshape(6, 1, H, H)
+    want = cube_pad.CubePad(pad, use_gpu=False)(x)[:, 0].numpy().astype(np.int32)
+    np.testing.assert_array_equal(ocp.index_map(H, H, pad), want)
+    np.testing.assert_array_equal(cp360_b200.cubepad_index_map(H, H, pad), want)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cubepad_values_multigroup_live(ref, seed):
+    """The batch loop over 6-face groups (cube_pad.py:38-41) on seeded float tensors, several channels."""
+    cube_pad = ref[0]
+    rng = np.random.default_rng(7000 + seed)
+    H = int(rng.integers(2, 12))
+    groups, C = int(rng.integers(1, 4)), int(rng.integers(1, 6))
+    pad = [int(v) for v in rng.integers(0, min(H, 4) + 1, size=4)]
+    x = rng.standard_normal((6 * groups, C, H, H)).astype(np.float32)
+    want = cube_pad.CubePad(pad, use_gpu=False)(torch.from_numpy(x)).numpy()
+    got = ocp.cubepad(x, pad)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("w,H,vfov", [(5, 16, 90), (9, 40, 90), (13, 36, 75), (20, 50, 60), (24, 96, 90), (32, 120, 80)])
+def test_e2c_maps_and_faces_live(ref, w, H, vfov):
+    """utils/equi_to_cube.py:12-129: float64 maps to 1e-9, the integer (1/32-px) maps and the resampled faces
+    bit-exact — oracle and cp360_e2c_build_map against the reference object."""
+    e2c_mod = ref[1]
+    W = 2 * H
+    img = np.random.default_rng(100 * w + H).random((H, W, 3), dtype=np.float32)
+    obj = e2c_mod.Equi2Cube(w, img, vfov=vfov)
+    ref_sx = np.stack([np.rint(a.astype(np.float32) * np.float32(32)).astype(np.int32).reshape(w, w) for a in obj.inXs])
+    ref_sy = np.stack([np.rint(a.astype(np.float32) * np.float32(32)).astype(np.int32).reshape(w, w) for a in obj.inYs])
+    inX, inY = oe2c.build_maps(w, H, W, vfov)
+    np.testing.assert_allclose(np.stack(inX), np.stack(obj.inXs), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.stack(inY), np.stack(obj.inYs), rtol=0, atol=1e-9)
+    sx, sy = oe2c.fixed_maps(w, H, W, vfov)
+    np.testing.assert_array_equal(sx.reshape(6, w, w), ref_sx)
+    np.testing.assert_array_equal(sy.reshape(6, w, w), ref_sy)
+    mine = cp360_b200.Equi2Cube(w, img, vfov=vfov)                     # host builder of the C-ABI
+    np.testing.assert_array_equal(mine.sx.reshape(6, w, w), ref_sx)
+    np.testing.assert_array_equal(mine.sy.reshape(6, w, w), ref_sy)
+    np.testing.assert_allclose(np.stack(mine.inXs), np.stack(obj.inXs), rtol=0, atol=1e-9)
+    faces = obj.to_cube(img)
+    want = np.stack([faces[i] for i in range(6)])
+    got = oe2c.to_cube(img, sx, sy)
+    assert got.dtype == want.dtype
+    np.testing.assert_array_equal(got.reshape(want.shape), want)
+
+
+@pytest.mark.parametrize("w,C", [(2, 3), (3, 4), (5, 2), (6, 7), (9, 3), (11, 2), (12, 5), (20, 2)])
+def test_c2e_maps_and_output_live(ref, w, C):
+    """utils/cube_to_equi.py:12-66: face map exact, out_coord to 1e-12, the host sampling plan's normaliser M, and
+    to_equi_nn (6 grid_sample passes + masked writes) within 4e-6 of the single-pass restatement."""
+    c2e_mod = ref[2]
+    obj = c2e_mod.Cube2Equi(w)
+    face, coord = oc2e.build_maps(w)
+    np.testing.assert_array_equal(face.astype(np.int64), obj.face_map.astype(np.int64))
+    np.testing.assert_allclose(coord, obj.out_coord, rtol=0, atol=1e-12)
+    mine = cp360_b200.Cube2Equi(w)
+    np.testing.assert_array_equal(mine.face_map.astype(np.int64), obj.face_map.astype(np.int64))
+    np.testing.assert_allclose(mine.out_coord, obj.out_coord, rtol=0, atol=1e-12)
+    assert mine.M == float(np.max(obj.out_coord.astype(np.float32)))
+    cube = np.random.default_rng(50 + w).standard_normal((6, C, w, w)).astype(np.float32)
+    want = obj.to_equi_nn(torch.from_numpy(cube)).detach().numpy()
+    got = oc2e.to_equi(cube, face, coord)
+    assert got.shape == want.shape == (1, C, 2 * w, 4 * w)
+    assert float(np.abs(got - want).max()) <= 4e-6
+    np.testing.assert_allclose(oc2e.to_equi_max(cube, face, coord).reshape(2 * w, 4 * w), want.max(axis=1)[0], rtol=0, atol=4e-6)
+
+
+def test_cubepad_reference_size_mismatch_behaviour(ref, capsys):
+    """N % 6 != 0: the reference prints 'CubePad size mismatch!' and exit()s (cube_pad.py:33-35); the C-ABI returns
+    CP360_ERR_SIZE_MISMATCH, which the host mirror raises as ValueError with the same words."""
+    cube_pad = ref[0]
+    with pytest.raises(SystemExit):
+        cube_pad.CubePad(1, use_gpu=False)(torch.zeros(5, 1, 4, 4))
+    assert "CubePad size mismatch!" in capsys.readouterr().out
+    assert _lib.lib().cp360_cubepad_fwd(None, None, 5, 1, 4, 4, 1, 1, 1, 1, 4, None) == 2
+    assert b"size mismatch" in _lib.lib().cp360_last_error()
