@@ -126,3 +126,29 @@ def test_cubepad_reference_size_mismatch_behaviour(ref, capsys):
     assert "CubePad size mismatch!" in capsys.readouterr().out
     assert _lib.lib().cp360_cubepad_fwd(None, None, 5, 1, 4, 4, 1, 1, 1, 1, 4, None) == 2
     assert b"size mismatch" in _lib.lib().cp360_last_error()
+
+
+def test_extractor_front_end_float64_vs_fp32_live(ref):
+    """static_model/dataset_feat_extractor.py:142-157 as shipped runs the front end in float64 (uint8/255.0 ->
+    to_cube -> im_norm -> astype(float32)); the B200 path computes in fp32 from the uint8 frame (BASELINE's fp32
+    configuration). This pins how far apart the two are: <= 2e-7 on the faces, <= 1e-6 after im_norm (the division
+    by std ~ 0.225 scales the difference) — far inside what the network's own fp32 convolutions resolve."""
+    e2c_mod = ref[1]
+    utils_mod = __import__("importlib").import_module("utils.utils")
+    w, H = 16, 64
+    u8 = np.random.default_rng(77).integers(0, 256, size=(H, 2 * H, 3), dtype=np.uint8)
+    img64 = np.array(u8) / 255.0                                       # :142
+    obj = e2c_mod.Equi2Cube(w, img64)
+    faces64 = obj.to_cube(img64)                                       # :145, float64 faces
+    assert faces64[0].dtype == np.float64
+    sx, sy = oe2c.fixed_maps(w, H, 2 * H)
+    img32 = u8.astype(np.float32) / np.float32(255)                    # cp360_e2c_fwd_u8's conversion
+    np.testing.assert_array_equal(img32, img64.astype(np.float32))     # == float32(u8 / 255.0) for every code
+    faces32 = oe2c.to_cube(img32, sx, sy)
+    ref_faces = np.stack([faces64[i] for i in range(6)])
+    assert float(np.abs(faces32.reshape(ref_faces.shape) - ref_faces).max()) <= 2e-7
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    ref_batch = np.stack([utils_mod.im_norm(faces64[i].copy(), mean, std) for i in range(6)]).astype(np.float32)   # :148-157
+    mine = (faces32.reshape(ref_faces.shape) - np.float32(mean)) / np.float32(std)
+    assert mine.dtype == np.float32
+    assert float(np.abs(mine - ref_batch).max()) <= 1e-6
