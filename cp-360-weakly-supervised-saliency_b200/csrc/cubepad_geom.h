@@ -56,7 +56,7 @@ struct CubePadGeom {
 // y = yr*r + yc*c + y0 ; x = xr*r + xc*c + x0
 struct AffineSrc { int face, yr, yc, y0, xr, xc, x0; };
 
-inline PlateMap make_plate(const AffineSrc& a, int H, int W) {
+inline PlateMap make_plate(const AffineSrc& a, int W) {
   PlateMap m;
   m.face = a.face;
   m.base = a.y0 * W + a.x0;
@@ -105,10 +105,10 @@ inline bool make_geom(int H, int W, int pl, int pr, int pt, int pd, CubePadGeom*
       /*R*/ {FB, 1, 0, 0, 0, 1, 0},               // back[:, :pr]
       /*T*/ {FR, 0, 1, 0, -1, 0, W - 1}};         // flip(right[:pr, :]^T, rows)
   for (int f = 0; f < 6; ++f) {
-    g->plate[P_TOP][f] = make_plate(top[f], H, W);
-    g->plate[P_DOWN][f] = make_plate(down[f], H, W);
-    g->plate[P_LEFT][f] = make_plate(left[f], H, W);
-    g->plate[P_RIGHT][f] = make_plate(right[f], H, W);
+    g->plate[P_TOP][f] = make_plate(top[f], W);
+    g->plate[P_DOWN][f] = make_plate(down[f], W);
+    g->plate[P_LEFT][f] = make_plate(left[f], W);
+    g->plate[P_RIGHT][f] = make_plate(right[f], W);
   }
   // make_cubepad_edge: td_pad > lr_pad -> repeat the l/r plate's row, else the t/d plate's column
   g->corner_uses_lr[0] = pt > pl;

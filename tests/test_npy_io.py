@@ -1,7 +1,6 @@
 """CPU: the native .npy reader / writer (SURVEY.md §8 row f4 — the on-disk formats either side of the
 path) against numpy itself: written files are byte-identical to numpy.save, numpy.save'd files of
 every supported dtype / format version read back as float32(array)."""
-import io
 import os
 
 import numpy as np
