@@ -4,10 +4,10 @@ tests/golden/_ref_loader.py) on the benchmark chain, next to bench.py's CPU port
 same thread count, one frame at a time — and check that both produce the same outputs while at it.
 
 The port is what `bench.py --impl reference` and the `cpu_baseline` leg time on the GPU box (the reference is pure
-Python and cannot travel there). This script is the evidence that the port is a fair — slightly favourable — stand-in
-for the reference's own CPU path:
+Python and cannot travel there). This script is the evidence that the port is a fair stand-in for the
+reference's own CPU path (same outputs, same speed):
 
-    python tools/compare_port_vs_reference.py [frames, default 5]  >  profiles/r01_port_vs_reference.txt
+    python tools/compare_port_vs_reference.py [frames, default 15]  >  profiles/r01_port_vs_reference.txt
 """
 import os
 import sys
@@ -62,19 +62,21 @@ def main(frames):
     print("outputs: e2c faces bit-identical, 19 CubePad outputs bit-identical, c2e+max max-abs diff %.1e"
           % float((sr.detach() - sp).abs().max()))
 
-    def clock(fn):
-        fn()
-        t0 = time.perf_counter()
-        for _ in range(frames):
-            fn()
-        return (time.perf_counter() - t0) / frames
-
-    t_ref, t_port = clock(ref_frame), clock(port_frame)
-    print("threads: torch %d, cv2 %s, host cpus %d" % (torch.get_num_threads(), port.threads(), os.cpu_count()))
-    print("unmodified reference : %7.1f ms per frame  (%.2f frames/s)" % (1e3 * t_ref, 1 / t_ref))
-    print("oracle/ref_port      : %7.1f ms per frame  (%.2f frames/s)" % (1e3 * t_port, 1 / t_port))
-    print("port / reference speed: %.2fx  (>= 1: the reported CPU baseline flatters the reference)" % (t_ref / t_port))
+    # interleaved, per-frame times, median and best: the host is shared, back-to-back blocks drift by +-20 %
+    ref_frame(), port_frame()
+    t_ref, t_port = [], []
+    for _ in range(frames):
+        t0 = time.perf_counter(); ref_frame(); t1 = time.perf_counter(); port_frame(); t2 = time.perf_counter()
+        t_ref.append(t1 - t0)
+        t_port.append(t2 - t1)
+    med = lambda v: sorted(v)[len(v) // 2]                                                # noqa: E731
+    print("threads: torch %d, cv2 %s, host cpus %d; %d interleaved frames each" % (torch.get_num_threads(), port.threads(),
+                                                                                  os.cpu_count(), frames))
+    print("unmodified reference : median %7.1f ms per frame (%.2f frames/s), best %7.1f ms" % (1e3 * med(t_ref), 1 / med(t_ref), 1e3 * min(t_ref)))
+    print("oracle/ref_port      : median %7.1f ms per frame (%.2f frames/s), best %7.1f ms" % (1e3 * med(t_port), 1 / med(t_port), 1e3 * min(t_port)))
+    print("port / reference speed: %.2fx by medians, %.2fx by best frames"
+          % (med(t_ref) / med(t_port), min(t_ref) / min(t_port)))
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 5)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 15)
