@@ -10,3 +10,11 @@ _spec = importlib.util.spec_from_file_location(
 _mod = importlib.util.module_from_spec(_spec)
 sys.modules["cp360_b200"] = _mod
 _spec.loader.exec_module(_mod)
+
+if __name__ == "__main__":
+    # the reference's own self-test (`python model/cube_pad.py`, cube_pad.py:257-262; BASELINE.json configs[0])
+    import numpy as np
+    import torch
+    aa = torch.FloatTensor(np.zeros([12, 64, 256, 256])).cuda()
+    cp = _mod.CubePad(2)
+    print(cp(aa).size())
