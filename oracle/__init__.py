@@ -21,4 +21,7 @@ pinned against outputs of the reference ITSELF, executed in the build container 
 /root/reference by ``tests/golden/make_golden.py``; the resulting fixtures live in
 ``tests/golden/*.npz|json`` and ``tests/test_oracle_golden.py`` checks the oracle against
 every one of them (bit-exact for CubePad and the integer maps, <=1e-6 for float maps).
+In the build container ``tests/test_oracle_vs_reference.py`` additionally runs the reference live on
+seeded random configurations, ``tests/test_golden_reproducible.py`` regenerates the fixtures, and
+``tests/golden/compare_port_vs_reference.py`` times ref_port next to the reference (same outputs, same speed).
 """

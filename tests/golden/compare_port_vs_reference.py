@@ -7,16 +7,17 @@ The port is what `bench.py --impl reference` and the `cpu_baseline` leg time on 
 Python and cannot travel there). This script is the evidence that the port is a fair stand-in for the
 reference's own CPU path (same outputs, same speed):
 
-    python tools/compare_port_vs_reference.py [frames, default 15]  >  profiles/r01_port_vs_reference.txt
+    python tests/golden/compare_port_vs_reference.py [frames, default 15]  >  profiles/r01_port_vs_reference.txt
 """
 import os
 import sys
 import time
 import warnings
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, HERE)
 warnings.filterwarnings("ignore")
 
 import numpy as np  # noqa: E402
