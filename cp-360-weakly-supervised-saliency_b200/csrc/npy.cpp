@@ -8,6 +8,7 @@
 // conversion the reference's torch.FloatTensor(np.load(...)) performs (test_temporal.py:70-78).
 // Writer: byte-identical to numpy.save(arr) of a C-contiguous float32 array (version 1.0 header,
 // padded to a multiple of 64 bytes), so files are interchangeable with the reference's.
+#include <ctype.h>
 #include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -40,6 +41,7 @@ int parse_header(FILE* fp, const char* path, NpyHeader* h) {
     return CP360_ERR_BAD_ARG;
   }
   const int major = pre[6];
+  if (pre[7] != 0) { set_error("%s: unsupported .npy version %d.%d", path, major, (int)pre[7]); return CP360_ERR_BAD_ARG; }
   size_t hlen = 0, pre_len = 10;
   if (major == 1) {
     hlen = (size_t)pre[8] | ((size_t)pre[9] << 8);
@@ -56,45 +58,88 @@ int parse_header(FILE* fp, const char* path, NpyHeader* h) {
   if (fread(&hdr[0], 1, hlen, fp) != hlen) { set_error("%s: truncated header", path); return CP360_ERR_BAD_ARG; }
   h->data_offset = (int64_t)(pre_len + hlen);
 
-  auto value_after = [&](const char* key) -> size_t {
-    size_t k = hdr.find(key);
-    if (k == std::string::npos) return k;
-    k = hdr.find(':', k + strlen(key));
-    if (k == std::string::npos) return k;
-    ++k;
-    while (k < hdr.size() && hdr[k] == ' ') ++k;
-    return k;
+  // The header is a Python dict literal; numpy evaluates it with ast.literal_eval and insists on exactly the keys
+  // descr / fortran_order / shape. Parse that grammar strictly (anything numpy would reject is rejected here):
+  //   '{' entry (',' entry)* [','] '}' spaces ['\n']      entry := str ':' (str | True | False | '(' ints ')')
+  size_t i = 0;
+  const size_t n = hdr.size();
+  auto ws = [&] { while (i < n && (hdr[i] == ' ' || hdr[i] == '\t' || hdr[i] == '\n')) ++i; };
+  auto bad = [&](const char* what) { set_error("%s: malformed header (%s)", path, what); return CP360_ERR_BAD_ARG; };
+  auto quoted = [&](std::string* out) -> bool {
+    if (i >= n || (hdr[i] != '\'' && hdr[i] != '"')) return false;
+    const char q = hdr[i++];
+    const size_t b = i;
+    while (i < n && hdr[i] != q) {
+      const unsigned char c = (unsigned char)hdr[i];
+      if (c < 0x20 || c > 0x7e || c == '\\') return false;     // plain printable ASCII only (no escapes in dtype strings)
+      ++i;
+    }
+    if (i >= n) return false;
+    *out = hdr.substr(b, i - b);
+    ++i;
+    return true;
   };
-  size_t k = value_after("'descr'");
-  if (k == std::string::npos || k >= hdr.size() || (hdr[k] != '\'' && hdr[k] != '"')) {
-    set_error("%s: header has no simple 'descr'", path);       // structured dtypes are not supported
-    return CP360_ERR_BAD_ARG;
+  bool have_descr = false, have_fortran = false, have_shape = false;
+  ws();
+  if (i >= n || hdr[i] != '{') return bad("no dict");
+  ++i;
+  for (;;) {
+    ws();
+    if (i < n && hdr[i] == '}') { ++i; break; }
+    std::string key;
+    if (!quoted(&key)) return bad("key");
+    ws();
+    if (i >= n || hdr[i] != ':') return bad("':'");
+    ++i;
+    ws();
+    if (key == "descr") {
+      if (have_descr || !quoted(&h->descr)) return bad("'descr' (structured dtypes are not supported)");
+      have_descr = true;
+    } else if (key == "fortran_order") {
+      if (have_fortran) return bad("duplicate key");
+      if (hdr.compare(i, 4, "True") == 0) { h->fortran = true; i += 4; }
+      else if (hdr.compare(i, 5, "False") == 0) { h->fortran = false; i += 5; }
+      else return bad("'fortran_order'");
+      if (i < n && (isalnum((unsigned char)hdr[i]) || hdr[i] == '_')) return bad("'fortran_order'");
+      have_fortran = true;
+    } else if (key == "shape") {
+      if (have_shape || i >= n || hdr[i] != '(') return bad("'shape'");
+      ++i;
+      int count = 0;
+      bool comma = true;                                        // a number may follow '(' or ','
+      for (;;) {
+        ws();
+        if (i < n && hdr[i] == ')') { ++i; break; }
+        if (!comma || i >= n || !isdigit((unsigned char)hdr[i])) return bad("'shape'");
+        int64_t v = 0;
+        const size_t b = i;
+        while (i < n && isdigit((unsigned char)hdr[i])) {
+          if (v > (INT64_MAX - 9) / 10) return bad("'shape' extent too large");
+          v = v * 10 + (hdr[i++] - '0');
+        }
+        if (i - b > 1 && hdr[b] == '0') return bad("'shape'");  // leading zeros are a Python syntax error
+        if (i < n && hdr[i] == 'L') ++i;                        // python-2 era long suffix
+        h->shape.push_back(v);
+        ++count;
+        ws();
+        comma = i < n && hdr[i] == ',';
+        if (comma) ++i;
+      }
+      if (count == 1 && !comma) return bad("'shape' is not a tuple");   // "(5)" is an int, numpy rejects it
+      have_shape = true;
+    } else {
+      return bad("unexpected key");
+    }
+    ws();
+    if (i < n && hdr[i] == ',') { ++i; continue; }
+    ws();
+    if (i < n && hdr[i] == '}') { ++i; break; }
+    return bad("',' or '}'");
   }
-  const size_t e = hdr.find(hdr[k], k + 1);
-  if (e == std::string::npos) { set_error("%s: malformed 'descr'", path); return CP360_ERR_BAD_ARG; }
-  h->descr = hdr.substr(k + 1, e - k - 1);
-  k = value_after("'fortran_order'");
-  if (k == std::string::npos) { set_error("%s: header has no 'fortran_order'", path); return CP360_ERR_BAD_ARG; }
-  h->fortran = hdr.compare(k, 4, "True") == 0;
-  k = value_after("'shape'");
-  if (k == std::string::npos || k >= hdr.size() || hdr[k] != '(') {
-    set_error("%s: header has no 'shape'", path);
-    return CP360_ERR_BAD_ARG;
-  }
-  const size_t close = hdr.find(')', k);
-  if (close == std::string::npos) { set_error("%s: malformed 'shape'", path); return CP360_ERR_BAD_ARG; }
-  const char* p = hdr.c_str() + k + 1;
-  const char* end = hdr.c_str() + close;
-  while (p < end) {
-    while (p < end && (*p == ' ' || *p == ',')) ++p;
-    if (p >= end) break;
-    char* q = nullptr;
-    const long long v = strtoll(p, &q, 10);
-    if (q == p || v < 0) { set_error("%s: malformed 'shape'", path); return CP360_ERR_BAD_ARG; }
-    h->shape.push_back((int64_t)v);
-    p = q;
-    while (p < end && *p == 'L') ++p;                           // python-2 era long suffix
-  }
+  while (i < n && hdr[i] == ' ') ++i;                        // numpy pads with spaces and ends the header with one '\n'
+  if (i < n && hdr[i] == '\n') ++i;
+  if (i != n) return bad("trailing characters");
+  if (!have_descr || !have_fortran || !have_shape) return bad("missing key");
   return CP360_OK;
 }
 
@@ -160,7 +205,10 @@ int cp360_npy_read_f32(const char* path, float* dst_host, int64_t n_elems) {
   int rc = parse_header(fp, path, &h);
   if (rc != CP360_OK) { fclose(fp); return rc; }
   int64_t n = 1;
-  for (int64_t v : h.shape) n *= v;
+  for (int64_t v : h.shape) {
+    if (v != 0 && n > INT64_MAX / v) { fclose(fp); set_error("%s: element count overflows", path); return CP360_ERR_RANGE; }
+    n *= v;
+  }
   const int es = elem_size_of(h.descr);
   if (h.fortran && h.shape.size() > 1) { fclose(fp); set_error("%s: fortran_order arrays are not supported", path); return CP360_ERR_SHAPE; }
   if (es == 0) { fclose(fp); set_error("%s: unsupported dtype '%s'", path, h.descr.c_str()); return CP360_ERR_BAD_ARG; }

@@ -98,3 +98,55 @@ def test_backproject_files_matches_oracle(tmp_path):
         got = np.load(o)
         assert got.shape == (14, 28) and got.dtype == np.float32            # test_temporal.py:86-88
         assert np.abs(got - oc2e.to_equi_max(cube, face, coord)).max() <= 1e-5
+
+
+def test_reader_survives_mutated_headers(tmp_path):
+    """Robustness of the native header parser (csrc/npy.cpp): 600 seeded byte-level mutations of valid files
+    (flips, insertions, deletions, truncations, in the header region or anywhere; hostile shapes) never crash the process;
+    whenever the native reader accepts a file numpy accepts it too and both yield the same values."""
+    rng = np.random.default_rng(20261017)
+    base = []
+    for shape, dtype, version in [((6, 10, 7, 7), np.float32, (1, 0)), ((14, 28), np.float64, (2, 0)),
+                                  ((5,), np.int32, (1, 0)), ((), np.float32, (1, 0)), ((3, 0, 2), np.uint8, (3, 0))]:
+        import numpy.lib.format as fmt
+        a = (rng.standard_normal(shape) * 10).astype(dtype)
+        p = tmp_path / ("base_%d.npy" % len(base))
+        with open(p, "wb") as f:
+            fmt.write_array(f, a, version=version)
+        base.append(open(p, "rb").read())
+    hostile = [b"\x93NUMPY\x01\x00\x46\x00{'descr': '<f4', 'fortran_order': False, 'shape': (4611686018427387904, 4), }   \n",
+               b"\x93NUMPY\x01\x00\x40\x00{'descr': '<f4', 'fortran_order': False, 'shape': (" + b"1," * 40 + b"), }\n",
+               b"\x93NUMPY\x01\x00\xff\xff{'descr': '<f4'", b"\x93NUMPY\x02\x00\xff\xff\xff\x7f", b"\x93NUMPY\x01\x00\x00\x00",
+               b"\x93NUMPY\x01\x00\x10\x00{'shape': (2,), }"]
+    accepted = 0
+    path = str(tmp_path / "mut.npy")
+    for i in range(600):
+        if i < len(hostile):
+            blob = hostile[i]
+        else:
+            blob = bytearray(base[int(rng.integers(len(base)))])
+            region = min(len(blob), 128) if i % 2 else len(blob)       # header region / anywhere (data bytes too)
+            for _ in range(int(rng.integers(1, 4))):
+                if len(blob) < 2:
+                    break
+                kind, pos = int(rng.integers(4)), int(rng.integers(min(region, len(blob))))
+                if kind == 0:
+                    blob[pos] = int(rng.integers(256))
+                elif kind == 1:
+                    blob.insert(pos, int(rng.integers(256)))
+                elif kind == 2:
+                    del blob[pos]
+                else:
+                    del blob[int(rng.integers(len(blob))):]
+            blob = bytes(blob)
+        with open(path, "wb") as f:
+            f.write(blob)
+        try:
+            got = cp360_b200.load_npy(path)
+        except (ValueError, RuntimeError, MemoryError, OverflowError):
+            continue
+        want = np.load(path, allow_pickle=False)                 # accepted natively => numpy must accept it too
+        assert tuple(got.shape) == want.shape, (i, blob[:96])
+        assert np.array_equal(got.numpy(), want.astype(np.float32), equal_nan=True), (i, blob[:96])
+        accepted += 1
+    assert accepted >= 20                                        # mutations in padding / data leave files valid
