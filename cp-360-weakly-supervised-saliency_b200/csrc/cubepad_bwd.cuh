@@ -62,7 +62,11 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       tma::mbar_init(&full[s], 1);
+#ifdef CP360_ARRIVE_ALL
+      tma::mbar_init(&empty[s], n_cons);               // diagnostic build: every consumer thread arrives (tools/racecheck_probe.py)
+#else
       tma::mbar_init(&empty[s], n_cons_warps);
+#endif
     }
     tma::fence_mbar_init();
   }
@@ -204,8 +208,12 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
         }
       }
     }
-    __syncwarp();
+#ifdef CP360_ARRIVE_ALL
+    tma::mbar_arrive(&empty[s]);
+#else
+    __syncwarp();                                      // orders every lane's reads of the stage before lane 0's release
     if (lane == 0) tma::mbar_arrive(&empty[s]);
+#endif
     if (++s == a.stages) { s = 0; ph ^= 1u; }
   }
 }

@@ -70,7 +70,11 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       tma::mbar_init(&full[s], 1);
+#ifdef CP360_ARRIVE_ALL
+      tma::mbar_init(&empty[s], n_cons);               // diagnostic build: every consumer thread arrives (tools/racecheck_probe.py)
+#else
       tma::mbar_init(&empty[s], n_cons_warps);
+#endif
     }
     tma::fence_mbar_init();
   }
@@ -185,8 +189,12 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
         for (; cc < kl; ++cc, sp += HW, dp += HoWo) __stcs(dp, EPI ? epi(*sp, cc) : *sp);
       }
     }
-    __syncwarp();
+#ifdef CP360_ARRIVE_ALL
+    tma::mbar_arrive(&empty[s]);
+#else
+    __syncwarp();                                      // orders every lane's reads of the stage before lane 0's release
     if (lane == 0) tma::mbar_arrive(&empty[s]);
+#endif
     if (++s == a.stages) { s = 0; ph ^= 1u; }
   }
 #ifdef CP360_TRACE

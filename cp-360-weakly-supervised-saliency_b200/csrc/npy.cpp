@@ -253,8 +253,14 @@ int cp360_npy_write_f32(const char* path, const float* src_host, int ndim, const
   if (n > 0 && !src_host) { set_error("npy: null data"); return CP360_ERR_BAD_ARG; }
   // numpy.lib.format: dict literal, then spaces so that magic+len+header is a multiple of 64, '\n' last
   std::string hdr = "{'descr': '<f4', 'fortran_order': False, 'shape': " + shp + ", }";
-  const size_t unpadded = 10 + hdr.size() + 1;
-  hdr.append((64 - unpadded % 64) % 64, ' ');
+  // numpy's _write_array_header: spare room so the first extent can grow in place (21 digits), then
+  // _wrap_header: padlen = 64 - ((magic + len field + header + '\n') % 64), i.e. 1..64 spaces, never 0
+  if (ndim > 0) {
+    const size_t digits = std::to_string((long long)shape[0]).size();
+    if (digits < 21) hdr.append(21 - digits, ' ');
+  }
+  const size_t hlen = hdr.size() + 1;
+  hdr.append(64 - ((10 + hlen) % 64), ' ');
   hdr.push_back('\n');
   if (hdr.size() > 65535) { set_error("npy: header too long for format 1.0"); return CP360_ERR_RANGE; }
   const std::string tmp = std::string(path) + ".tmp~";

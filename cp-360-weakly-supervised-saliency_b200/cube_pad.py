@@ -67,11 +67,30 @@ def cubepad_forward(x, pads, algo=_lib.ALGO_AUTO):
     return y
 
 
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
 def cubepad_fused(x, pads, scale=None, shift=None, relu=False, out=None, out_channel_offset=0):
     """CubePad(act(x * scale[c] + shift[c])) in ONE pass (fp32): the eval-mode BatchNorm affine and
     ReLU that precede CubePad in the cubic ResNet (model/resnet_cubic.py:89-92) never cost a tensor
     round trip of their own. `out` [6N,Cout,Ho,Wo] with Cout >= C lets several sources land in one
-    padded tensor (see cubepad_cat). Separate multiply and add: bit-exact against numpy fp32."""
+    padded tensor (see cubepad_cat). Separate multiply and add: bit-exact against numpy fp32.
+
+    Differentiable in x, scale and shift (backward = cp360_cubepad_bwd_f32, then the ReLU mask and
+    the affine's chain rule) — except with a caller-supplied `out` window, which autograd cannot
+    track: that form raises when a gradient is required (use cubepad_cat, which is differentiable)."""
+    if _needs_grad(x, scale, shift):
+        if out is not None:
+            raise RuntimeError("cubepad_fused(out=...) writes a channel window in place and is not differentiable; "
+                               "use cubepad_cat([...]) or call it under torch.no_grad()")
+        as_t = lambda v: None if v is None else (v if isinstance(v, torch.Tensor) else  # noqa: E731
+                                                 torch.as_tensor(v, dtype=torch.float32, device=x.device))
+        return _CubePadFusedFn.apply(x, as_t(scale), as_t(shift), tuple(pads), bool(relu))
+    return _cubepad_fused_raw(x, pads, scale, shift, relu, out, out_channel_offset)
+
+
+def _cubepad_fused_raw(x, pads, scale=None, shift=None, relu=False, out=None, out_channel_offset=0):
     _require_cuda(x, "cubepad_fused")
     if x.dim() != 4 or x.dtype != torch.float32:
         raise ValueError("cubepad_fused expects a float32 [6N, C, H, W] tensor")
@@ -108,8 +127,17 @@ def cubepad_fused(x, pads, scale=None, shift=None, relu=False, out=None, out_cha
 
 def cubepad_cat(tensors, lrtd_pad):
     """CubePad(torch.cat(tensors, 1)) without materialising the concatenation (model/clstm.py:57-58):
-    every source is read once and written straight into its channel window of the padded tensor."""
+    every source is read once and written straight into its channel window of the padded tensor.
+    Differentiable: the ConvLSTM trains through this site (train_temporal.py:100-107,167-170), so each
+    source receives cp360_cubepad_bwd_f32 of its channel window of the output gradient."""
     pads = get_pad_size(lrtd_pad)
+    tensors = list(tensors)
+    if _needs_grad(*tensors):
+        return _CubePadCatFn.apply(pads, *tensors)
+    return _cubepad_cat_raw(tensors, pads)
+
+
+def _cubepad_cat_raw(tensors, pads):
     p_l, p_r, p_t, p_d = pads
     n, _, h, w = tensors[0].shape
     ctot = sum(int(t.shape[1]) for t in tensors)
@@ -118,7 +146,7 @@ def cubepad_cat(tensors, lrtd_pad):
     for t in tensors:
         if t.shape[0] != n or t.shape[2] != h or t.shape[3] != w:
             raise ValueError("cubepad_cat: tensors must agree in every dimension but channels")
-        cubepad_fused(t, pads, out=out, out_channel_offset=off)
+        _cubepad_fused_raw(t, pads, out=out, out_channel_offset=off)
         off += int(t.shape[1])
     return out
 
@@ -145,6 +173,58 @@ def cubepad_backward(gy, pads, in_hw):
         _lib.check(_lib.lib().cp360_cubepad_bwd_f32(
             g32.data_ptr(), gx.data_ptr(), n, c, h, w, p_l, p_r, p_t, p_d, st))
     return gx if gy.dtype == torch.float32 else gx.to(gy.dtype)
+
+
+class _CubePadFusedFn(torch.autograd.Function):
+    """y = CubePad(act(x * scale + shift)); dL/dx, dL/dscale, dL/dshift through the pad's transpose."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, pads, relu):
+        ctx.pads, ctx.relu, ctx.in_hw = pads, relu, (x.shape[2], x.shape[3])
+        ctx.save_for_backward(x, scale if isinstance(scale, torch.Tensor) else None,
+                              shift if isinstance(shift, torch.Tensor) else None)
+        return _cubepad_fused_raw(x.detach(), pads, None if scale is None else scale.detach(),
+                                  None if shift is None else shift.detach(), relu)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, scale, shift = ctx.saved_tensors
+        ga = cubepad_backward(gy, ctx.pads, ctx.in_hw)              # gradient w.r.t. act(z), z = x * scale + shift
+        c = x.shape[1]
+        sc = None if scale is None else scale.float().reshape(1, c, 1, 1)
+        if ctx.relu:
+            z = x if sc is None else x * sc
+            if shift is not None:
+                z = z + shift.float().reshape(1, c, 1, 1)
+            ga = ga * (z > 0)
+        gx = gscale = gshift = None
+        if ctx.needs_input_grad[0]:
+            gx = ga if sc is None else ga * sc
+        if scale is not None and ctx.needs_input_grad[1]:
+            gscale = (ga * x).sum((0, 2, 3)).reshape(scale.shape).to(scale.dtype)
+        if shift is not None and ctx.needs_input_grad[2]:
+            gshift = ga.sum((0, 2, 3)).reshape(shift.shape).to(shift.dtype)
+        return gx, gscale, gshift, None, None
+
+
+class _CubePadCatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pads, *tensors):
+        ctx.pads = pads
+        ctx.in_hw = (tensors[0].shape[2], tensors[0].shape[3])
+        ctx.channels = [int(t.shape[1]) for t in tensors]
+        return _cubepad_cat_raw([t.detach() for t in tensors], pads)
+
+    @staticmethod
+    def backward(ctx, gy):
+        grads, off = [], 0
+        for i, c in enumerate(ctx.channels):
+            g = None
+            if ctx.needs_input_grad[1 + i]:
+                g = cubepad_backward(gy[:, off:off + c].contiguous(), ctx.pads, ctx.in_hw)
+            grads.append(g)
+            off += c
+        return (None, *grads)
 
 
 class _CubePadFn(torch.autograd.Function):

@@ -35,8 +35,12 @@ def load_npy(path, out=None, pin=False):
     n = int(np.prod(shape, dtype=np.int64)) if shape else 1
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, pin_memory=bool(pin and torch.cuda.is_available()))
-    elif out.dtype != torch.float32 or out.numel() != n or not out.is_contiguous() or out.is_cuda:
-        raise ValueError("out must be a contiguous float32 host tensor of %d elements" % n)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.is_cuda:
+        raise ValueError("out must be a contiguous float32 host tensor")
+    elif tuple(out.shape) != tuple(shape) and not (out.dim() == 1 and out.numel() == n):
+        # a flat buffer of the right size is fine; the same element count in another layout (e.g. a
+        # [6,7,7,1000] file into a [6,1000,7,7] buffer) must not be reinterpreted silently
+        raise ValueError("%s holds an array of shape %s, out has shape %s" % (path, tuple(shape), tuple(out.shape)))
     _lib.check(_lib.lib().cp360_npy_read_f32(os.fsencode(path), out.data_ptr(), n))
     return out
 
@@ -59,11 +63,13 @@ def load_cube_feat(path, out=None, pin=False):
     return t
 
 
-def backproject_files(feat_paths, out_paths, device=None, batch=16, square=False):
+def backproject_files(feat_paths, out_paths, device=None, batch=16, square=False, align_corners=False):
     """Score files -> saliency files: for every `cube_feat` file, Cube2Equi + channel max
     (test_temporal.py:82-88 without the ConvLSTM in between; dataset_feat_extractor.py:174-176 with
     ``square=True``). Files are read into pinned buffers, moved and processed ``batch`` at a time on the
-    GPU, and written back with the native writer. Returns the number of maps written."""
+    GPU, and written back with the native writer. Returns the number of maps written.
+    align_corners: grid_sample convention of the back-projection (Cube2Equi docstring); every file's own
+    header is checked against the batch's shape."""
     from .cube_to_equi import Cube2Equi
     if len(feat_paths) != len(out_paths):
         raise ValueError("feat_paths and out_paths differ in length")
@@ -78,7 +84,7 @@ def backproject_files(feat_paths, out_paths, device=None, batch=16, square=False
             raise ValueError("%s: expected cube scores [6,C,w,w], got %s" % (chunk[0], shape))
         if stage is None or tuple(stage.shape[1:]) != shape or stage.shape[0] < len(chunk):
             stage = torch.empty((batch,) + shape, dtype=torch.float32).pin_memory()
-            c2e = Cube2Equi(shape[2]) if c2e is None or c2e.input_w != shape[2] else c2e
+            c2e = Cube2Equi(shape[2], align_corners=align_corners) if c2e is None or c2e.input_w != shape[2] else c2e
         for j, p in enumerate(chunk):
             load_cube_feat(p, out=stage[j])
         x = stage[:len(chunk)].to(dev, non_blocking=True).reshape((6 * len(chunk),) + shape[1:])

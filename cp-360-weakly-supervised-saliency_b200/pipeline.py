@@ -105,9 +105,11 @@ def prefer_gpu_numa_node(device):
 
 class SphericalPipeline:
     def __init__(self, equi_h=960, equi_w=1920, cube=256, cam_channels=1000, feat_channels=2048,
-                 device=None, seed=1234, fuse_first_site=False):
+                 device=None, seed=1234, fuse_first_site=False, align_corners=False):
         """fuse_first_site: run e2c and the CubePad(3) in front of conv1 as ONE kernel
-        (cp360_e2c_cubepad_fwd); the unpadded faces are then never written."""
+        (cp360_e2c_cubepad_fwd); the unpadded faces are then never written.
+        align_corners: grid_sample convention of the back-projection (False = what the unmodified reference
+        computes under the installed torch; True = the torch<=1.2 behaviour it was written against)."""
         self.fuse_first_site = bool(fuse_first_site)
         if not torch.cuda.is_available():
             raise RuntimeError("SphericalPipeline needs a CUDA device (sm_100a); no CPU fallback")
@@ -118,7 +120,7 @@ class SphericalPipeline:
         self.feat_w = self.cube // 32
         self.cam_channels, self.feat_channels = int(cam_channels), int(feat_channels)
         self.e2c = Equi2Cube(self.cube, np.empty((self.equi_h, self.equi_w, 3), np.float32))
-        self.c2e = Cube2Equi(self.feat_w)
+        self.c2e = Cube2Equi(self.feat_w, align_corners=align_corners)
         self.sites = resnet50_cubepad_sites(self.cube) + [(self.feat_channels, self.feat_w, 1)]
         self.seed = seed
         self.B = 0

@@ -272,6 +272,63 @@ def test_cubepad_backward_matches_autograd(dev):
         np.testing.assert_array_equal(ones.cpu().numpy().reshape(shape[0] // 6, 6, shape[1], shape[2], shape[3]), want)
 
 
+def test_cubepad_fused_ops_are_differentiable(dev):
+    """cubepad_cat / cubepad_fused / cubepad_bn_relu sit on the training path when a maintainer adopts them
+    (clstm.py:57-58 under train_temporal.py:167-170): gradients must reach every source, scale and shift —
+    checked against autograd over the unfused torch formulation."""
+    torch.manual_seed(21)
+    # cat + CubePad: both sources receive their window of the transposed pad
+    a = torch.randn((12, 6, 7, 7), device=dev, requires_grad=True)
+    b = torch.randn((12, 10, 7, 7), device=dev, requires_grad=True)
+    y = cp360_b200.cubepad_cat([a, b], 1)
+    assert y.grad_fn is not None
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    a2, b2 = a.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    gather_reference(torch.cat([a2, b2], 1), ocp.index_map(7, 7, 1)).backward(gy)
+    torch.testing.assert_close(a.grad, a2.grad, rtol=0, atol=1e-5)
+    torch.testing.assert_close(b.grad, b2.grad, rtol=0, atol=1e-5)
+    # only one source needs a gradient
+    c = torch.randn((12, 10, 7, 7), device=dev)
+    a3 = a.detach().clone().requires_grad_(True)
+    cp360_b200.cubepad_cat([a3, c], 1).backward(gy)
+    torch.testing.assert_close(a3.grad, a2.grad, rtol=0, atol=1e-5)
+    # affine + ReLU + CubePad: x, scale, shift
+    x = torch.randn((6, 8, 16, 16), device=dev, requires_grad=True)
+    sc = (torch.rand(8, device=dev) + 0.5).requires_grad_(True)
+    sh = torch.randn(8, device=dev, requires_grad=True)
+    y = cp360_b200.cubepad_fused(x, (1, 1, 1, 1), scale=sc, shift=sh, relu=True)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x2, sc2, sh2 = (t.detach().clone().requires_grad_(True) for t in (x, sc, sh))
+    z = torch.relu(x2 * sc2.view(1, -1, 1, 1) + sh2.view(1, -1, 1, 1))
+    y2 = gather_reference(z, ocp.index_map(16, 16, 1))
+    assert torch.equal(y.detach(), y2.detach())
+    y2.backward(gy)
+    torch.testing.assert_close(x.grad, x2.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(sc.grad, sc2.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(sh.grad, sh2.grad, rtol=1e-4, atol=1e-4)
+    # a caller-supplied output window cannot be tracked: loud error instead of a silently dropped gradient
+    out = torch.empty((6, 8, 18, 18), device=dev)
+    with pytest.raises(RuntimeError):
+        cp360_b200.cubepad_fused(x, (1, 1, 1, 1), out=out)
+    with torch.no_grad():
+        cp360_b200.cubepad_fused(x, (1, 1, 1, 1), out=out)
+    # eval-mode BN folded into the pad: gradient w.r.t. the input
+    bn = torch.nn.BatchNorm2d(8).to(dev).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.normal_()
+        bn.bias.normal_()
+    x3 = x.detach().clone().requires_grad_(True)
+    y = cp360_b200.cubepad_bn_relu(x3, bn, 1)
+    y.backward(gy)
+    x4 = x.detach().clone().requires_grad_(True)
+    cp360_b200.CubePad(1)(torch.relu(bn(x4))).backward(gy)
+    torch.testing.assert_close(x3.grad, x4.grad, rtol=1e-4, atol=1e-5)
+
+
 @pytest.mark.parametrize("shape,pad", [((12, 2000, 7, 7), 1), ((6, 4000, 7, 7), 1), ((12, 2048, 8, 8), 1), ((6, 64, 16, 16), 1),
                                        ((6, 16, 32, 32), 1), ((12, 8, 14, 14), 3), ((6, 8, 9, 9), [4, 2, 3, 5]),
                                        ((6, 4, 12, 12), [1, 2, 3, 0]), ((6, 7, 8, 8), 2), ((6, 3, 7, 7), 1),

@@ -23,6 +23,28 @@ def test_writer_is_byte_identical_to_numpy_save(tmp_path, shape):
     assert not os.path.exists(ours + ".tmp~")
 
 
+def test_writer_header_padding_matches_numpy_for_every_header_length(tmp_path):
+    """numpy pads in two steps (21-digit growth room for the first extent, then 1..64 spaces up to a 64 B boundary,
+    never 0): sweep header lengths across the boundaries with zero-size arrays of 1..14 dims and extents of 1..10
+    digits, including the exactly-aligned case and headers longer than 128 bytes."""
+    rng = np.random.default_rng(11)
+    seen = set()
+    for i in range(300):
+        nd = int(rng.integers(1, 15))
+        shape = [int(rng.integers(1, 4)) for _ in range(nd)]            # product stays far below 2**63
+        shape[int(rng.integers(nd))] = int(10 ** int(rng.integers(0, 10)) * int(rng.integers(1, 10)))
+        shape[int(rng.integers(nd))] = 0                       # no data: extents are free
+        a = np.empty(tuple(shape), np.float32)
+        ours, theirs = str(tmp_path / "o.npy"), str(tmp_path / "t.npy")
+        cp360_b200.save_npy(ours, a)
+        np.save(theirs, a)
+        bo, bt = open(ours, "rb").read(), open(theirs, "rb").read()
+        assert bo == bt, shape
+        seen.add(len(bt))
+        assert cp360_b200.npy_header(ours)[1] == tuple(shape)
+    assert {128, 192} <= seen
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.float16, np.uint8, np.int32, np.int64])
 def test_reader_converts_like_float_tensor(tmp_path, dtype):
     rng = np.random.default_rng(7)
@@ -38,6 +60,8 @@ def test_reader_converts_like_float_tensor(tmp_path, dtype):
     np.testing.assert_array_equal(got.numpy(), a.astype(np.float32))       # == torch.FloatTensor(np.load(path))
     buf = torch.empty(a.size)
     assert cp360_b200.load_npy(path, out=buf) is buf
+    with pytest.raises(ValueError):                    # same element count, different layout: refused
+        cp360_b200.load_npy(path, out=torch.empty((6, 7, 7, 10)))
     np.testing.assert_array_equal(buf.numpy().reshape(a.shape), a.astype(np.float32))
 
 
