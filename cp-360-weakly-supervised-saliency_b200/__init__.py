@@ -10,16 +10,17 @@ plus SphericalPipeline (pipeline.py), the batched, frame-sharded chain the bench
 """
 from . import _lib
 from ._build import build_library, LIB_PATH
-from .cube_pad import (CubePad, CubePadding, get_pad_size, cubepad_forward, cubepad_index_map, cubepad_fused,
+from .cube_pad import (autotune_cubepad, CubePad, CubePadding, get_pad_size, cubepad_forward, cubepad_index_map, cubepad_fused,
                        cubepad_cat, cubepad_bn_relu)
 from .cam import SaliencyHead, cam_scores, cam_weight
 from .cube_to_equi import Cube2Equi
 from .equi_to_cube import Equi2Cube
+from .hostmem import pinned_empty
 from .io import backproject_files, load_cube_feat, load_npy, npy_header, save_npy
-from .pipeline import (SphericalPipeline, gather_maps, gpu_numa_node, prefer_gpu_numa_node,
+from .pipeline import (SphericalPipeline, TemporalCubePadSequence, gather_maps, gpu_numa_node, prefer_gpu_numa_node,
                        resnet50_cubepad_sites, shard_range)
 
-__all__ = ["CubePad", "CubePadding", "get_pad_size", "cubepad_forward", "cubepad_index_map", "cubepad_fused", "cubepad_cat", "cubepad_bn_relu",
-           "Equi2Cube", "Cube2Equi", "SaliencyHead", "cam_scores", "cam_weight", "SphericalPipeline", "gather_maps", "resnet50_cubepad_sites",
+__all__ = ["CubePad", "CubePadding", "get_pad_size", "cubepad_forward", "cubepad_index_map", "cubepad_fused", "cubepad_cat", "cubepad_bn_relu", "autotune_cubepad",
+           "Equi2Cube", "Cube2Equi", "SaliencyHead", "cam_scores", "cam_weight", "SphericalPipeline", "TemporalCubePadSequence", "gather_maps", "resnet50_cubepad_sites",
            "shard_range", "build_library", "LIB_PATH", "load_npy", "save_npy", "npy_header", "load_cube_feat",
-           "backproject_files"]
+           "backproject_files", "pinned_empty"]

@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.environ.get("CP360_LIB") or os.path.join(LIB_DIR, "libcp360.so")   # CP360_LIB: dev override
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
-CU_SOURCES = ["common.cu", "cubepad.cu", "e2c.cu", "c2e.cu"]
+CU_SOURCES = ["common.cu", "cubepad.cu", "e2c.cu", "c2e.cu", "hostmem.cu"]
 CPP_SOURCES = ["maps.cpp", "npy.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

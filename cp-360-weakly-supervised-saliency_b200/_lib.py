@@ -24,9 +24,11 @@ SIGNATURES = {
     "cp360_cubepad_fwd_algo": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 8 + [c_vp]),
     "cp360_cubepad_pick_algo": (c_i32, [c_i64, c_i64] + [c_i32] * 8),
     "cp360_cubepad_fused_fwd": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 6 + [c_vp, c_vp, c_i32, c_i64, c_i64, c_vp]),
+    "cp360_cubepad_autotune": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 7 + [c_vp]),
     "cp360_cubepad_tune_info": (c_i32, [c_i64, c_i64] + [c_i32] * 6 + [ctypes.c_char_p, c_i32]),
     "cp360_cubepad_build_inverse_map": (c_i32, [c_i32] * 6 + [c_vp, c_vp]),
     "cp360_cubepad_bwd_f32": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 6 + [c_vp]),
+    "cp360_e2c_map_words": (c_i64, [c_i32, c_i32, c_i32]),
     "cp360_e2c_build_map": (c_i32, [c_i32, c_i32, c_i32, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cp360_e2c_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp360_e2c_fwd_u8": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp, c_vp, c_vp]),
@@ -40,6 +42,8 @@ SIGNATURES = {
     "cp360_c2e_build_cubic_plan": (c_i32, [c_i32, c_vp]),
     "cp360_c2e_cubic_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
     "cp360_c2e_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "cp360_host_alloc": (c_i32, [ctypes.c_uint64, c_i32, ctypes.POINTER(c_vp)]),
+    "cp360_host_free": (c_i32, [c_vp]),
     "cp360_npy_read_header": (c_i32, [ctypes.c_char_p, ctypes.c_char_p, c_i32, p_i32, c_vp, c_i32, c_vp, p_i32]),
     "cp360_npy_read_f32": (c_i32, [ctypes.c_char_p, c_vp, c_i64]),
     "cp360_npy_write_f32": (c_i32, [ctypes.c_char_p, c_vp, c_i32, c_vp]),

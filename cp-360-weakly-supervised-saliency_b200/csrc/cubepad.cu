@@ -19,6 +19,7 @@
 // The geometry is the 4x6 affine plate table of cubepad_geom.h, identical for all kernels and
 // for the host-side index map exported to the parity tests.
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -31,6 +32,7 @@
 #include "cubepad_row.cuh"
 #include "cubepad_cube.cuh"
 #include "cubepad_bwd.cuh"
+#include "cubepad_tuned.h"
 
 namespace cp360 {
 
@@ -505,6 +507,7 @@ struct TuneCfg {
   int row_rb = 0, row_order1 = 0 /* order + 1 */, row_slots = 0, row_tile_kb = 0;
   int cube_stage_kb = 0, cube_stages = 0, cube_warps = 0;
   float us = 0.f;
+  int from_table = 0;       // > 0: a row of the built-in table measured at this many frames per launch
 };
 static thread_local const TuneCfg* t_tune = nullptr;
 
@@ -549,7 +552,9 @@ static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* 
   a->out_C = C; a->out_coff = 0; a->scale = nullptr; a->shift = nullptr; a->relu = 0;
   a->stage_words = 6 * kmax * HW;
   a->lut_off = 3 * kCubeMaxStages * 8;
-  a->ring_off = (a->lut_off + 6 * HoWo * 4 + 127) & ~127;
+  a->epi_off = (a->lut_off + 6 * HoWo * 4 + 15) & ~15;
+  const bool epi = t_fused && (t_fused->scale || t_fused->shift || t_fused->relu);
+  a->ring_off = (a->epi_off + (epi ? stages * 2 * kmax * 4 : 0) + 127) & ~127;
   const size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
   if (smem > 220 * 1024) return false;
   *smem_out = smem;
@@ -580,13 +585,13 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   CP360_CUBE_CASE(28, 1) CP360_CUBE_CASE(28, 2) CP360_CUBE_CASE(28, 4)
   CP360_CUBE_CASE(16, 4) CP360_CUBE_CASE(16, 8) CP360_CUBE_CASE(16, 16)
   CP360_CUBE_CASE(14, 4) CP360_CUBE_CASE(14, 8) CP360_CUBE_CASE(14, 16)
-  CP360_CUBE_CASE(8, 16) CP360_CUBE_CASE(8, 32) CP360_CUBE_CASE(7, 16) CP360_CUBE_CASE(7, 32)
+  CP360_CUBE_CASE(8, 16) CP360_CUBE_CASE(8, 32) CP360_CUBE_CASE(8, 64) CP360_CUBE_CASE(7, 16) CP360_CUBE_CASE(7, 32) CP360_CUBE_CASE(7, 64)
 #undef CP360_CUBE_CASE
 #define CP360_CUBE_K(KK) \
   case KK: kern = epi ? cubepad_cube2_kernel<0, 0, KK, true> : cubepad_cube2_kernel<0, 0, KK, false>; break;
   if (!kern) {
     switch (a.kmax) {
-      CP360_CUBE_K(1) CP360_CUBE_K(2) CP360_CUBE_K(4) CP360_CUBE_K(8) CP360_CUBE_K(16) CP360_CUBE_K(32)
+      CP360_CUBE_K(1) CP360_CUBE_K(2) CP360_CUBE_K(4) CP360_CUBE_K(8) CP360_CUBE_K(16) CP360_CUBE_K(32) CP360_CUBE_K(64)
       default: kern = epi ? cubepad_cube2_kernel<0, 0, 0, true> : cubepad_cube2_kernel<0, 0, 0, false>; break;
     }
   }
@@ -785,7 +790,7 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
 #define CP360_ROW_CASE(NJ_, FULL_) \
   if (nj == NJ_ && full == FULL_) kern = epi ? cubepad_row_kernel<NJ_, FULL_, true> : cubepad_row_kernel<NJ_, FULL_, false>;
   CP360_ROW_CASE(1, true) CP360_ROW_CASE(1, false) CP360_ROW_CASE(2, true) CP360_ROW_CASE(2, false)
-  CP360_ROW_CASE(4, true) CP360_ROW_CASE(4, false) CP360_ROW_CASE(7, false) CP360_ROW_CASE(8, true)
+  CP360_ROW_CASE(4, true) CP360_ROW_CASE(4, false) CP360_ROW_CASE(7, true) CP360_ROW_CASE(7, false) CP360_ROW_CASE(8, true)
 #undef CP360_ROW_CASE
   int per_sm = std::max(1, std::min(2048 / kRowThreads, (int)((224 * 1024) / (smem + 1024))));
   per_sm = std::min(per_sm, std::max(1, env_int("CP360_ROW_CTAS", 1)));
@@ -857,10 +862,32 @@ static TuneKey tune_key(const CubePadGeom& g, int64_t n_faces, int C) {
 }
 
 static bool tuned_lookup(const TuneKey& k, TuneCfg* out) {
-  std::lock_guard<std::mutex> lock(g_tuned_mutex);
-  auto it = g_tuned.find(k);
-  if (it == g_tuned.end()) return false;
-  *out = it->second;
+  {
+    std::lock_guard<std::mutex> lock(g_tuned_mutex);
+    auto it = g_tuned.find(k);
+    if (it != g_tuned.end()) { *out = it->second; return true; }
+  }
+  // built-in table (cubepad_tuned.h, generated on a B200 by tools/tune_table.py): symmetric pads, exact
+  // (H, pad, C); among the batch sizes measured for that site the one nearest in log2 to this launch's
+  if (k.pl != k.pr || k.pl != k.pt || k.pl != k.pd || k.n_faces <= 0) return false;
+  static const bool use_table = env_int("CP360_TUNED_TABLE", 1) != 0;
+  if (!use_table) return false;
+  const TunedRow* best = nullptr;
+  double best_d = 1e30;
+  const double want = log2((double)k.n_faces / 6.0);
+  for (const TunedRow& r : kTunedTable) {
+    if (r.H != k.H || r.p != k.pl || r.C != k.C) continue;
+    const double d = fabs(log2((double)r.frames) - want);
+    if (d < best_d) { best_d = d; best = &r; }
+  }
+  if (!best) return false;
+  TuneCfg c;
+  c.algo = best->algo;
+  c.row_rb = best->row_rb; c.row_order1 = best->row_order1; c.row_slots = best->row_slots; c.row_tile_kb = best->row_tile_kb;
+  c.cube_stage_kb = best->cube_stage_kb; c.cube_stages = best->cube_stages; c.cube_warps = best->cube_warps;
+  c.us = best->us;
+  c.from_table = best->frames;
+  *out = c;
   return true;
 }
 
@@ -879,10 +906,25 @@ static std::vector<TuneCfg> tune_candidates(const CubePadGeom& g, int64_t n_face
   RowArgs ra; Cube2Args ca; size_t smem; int per_sm;
   if (g.H >= 24 && row_plan(g, n_faces * C, C, &ra)) {
     if (HW * 4 > 6144) {                                        // bands of rows: band height x dealing order
+      // equal-height bands only (a short last band pays the full per-tile cost for a fraction of the bytes):
+      // H / n rows for every band count n whose tile lands between ~2.5 and ~8 KB; narrow rows are copied four
+      // at a time, so their band heights are also tried rounded up to a multiple of four
       std::vector<int> rbs;
-      for (int bytes : {3072, 3584, 4096, 4608, 5120, 6144}) {
-        const int rb = std::max(1, (bytes + g.W * 2) / (g.W * 4));
-        if (rb < g.H && std::find(rbs.begin(), rbs.end(), rb) == rbs.end()) rbs.push_back(rb);
+      auto add = [&](int rb) {
+        if (rb >= 1 && rb < g.H && rb * g.W * 4 >= 2560 && rb * g.W * 4 <= 8192 &&
+            std::find(rbs.begin(), rbs.end(), rb) == rbs.end()) rbs.push_back(rb);
+      };
+      for (int n = 2; n <= g.H; ++n) {
+        const int rb = (g.H + n - 1) / n;
+        add(rb);
+        if (g.W < 128) add((rb + 3) / 4 * 4);
+      }
+      if (rbs.empty()) rbs.push_back(std::max(1, 4608 / (g.W * 4)));
+      if (rbs.size() > 10) {                                    // keep the tuning pass short: thin out evenly
+        std::vector<int> keep;
+        for (size_t i = 0; i < 10; ++i) keep.push_back(rbs[i * (rbs.size() - 1) / 9]);
+        keep.erase(std::unique(keep.begin(), keep.end()), keep.end());
+        rbs.swap(keep);
       }
       for (int rb : rbs)
         for (int order : {0, 2}) {
@@ -913,7 +955,7 @@ static std::vector<TuneCfg> tune_candidates(const CubePadGeom& g, int64_t n_face
 
 // Returns true and fills *best if tuning ran (y then holds the result of a complete launch).
 static bool autotune(const void* x, void* y, int64_t n_faces, int C, const CubePadGeom& g, cudaStream_t st,
-                     TuneCfg* best) {
+                     TuneCfg* best, int effort = 1) {
   std::vector<TuneCfg> cands = tune_candidates(g, n_faces, C);
   if (cands.size() < 2) return false;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -940,7 +982,7 @@ static bool autotune(const void* x, void* y, int64_t n_faces, int C, const CubeP
     }
     return best_ms;
   };
-  for (size_t i = 0; i < cands.size(); ++i) cands[i].us = time_cfg(cands[i], 2) * 1e3f;
+  for (size_t i = 0; i < cands.size(); ++i) cands[i].us = time_cfg(cands[i], 2 * effort) * 1e3f;
   // event timing is quantised (~2 us) and noisy: re-time the front-runners with more repetitions
   std::vector<size_t> idx(cands.size());
   for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
@@ -949,14 +991,14 @@ static bool autotune(const void* x, void* y, int64_t n_faces, int C, const CubeP
   for (size_t r = 0; r < std::min<size_t>(4, idx.size()); ++r) {
     TuneCfg& c = cands[idx[r]];
     if (c.us > 1e29f) continue;
-    c.us = std::min(c.us, time_cfg(c, 5) * 1e3f);
+    c.us = std::min(c.us, time_cfg(c, 5 * effort) * 1e3f);
     if (bi < 0 || c.us < cands[bi].us) bi = (int)idx[r];
   }
   if (bi >= 0 && cands[bi].algo == ALGO_ROW) {                  // ring depth around the winner
     for (int slots : {2, 4}) {
       TuneCfg c = cands[bi];
       c.row_slots = slots;
-      const float ms = time_cfg(c, 3);
+      const float ms = time_cfg(c, 3 * effort);
       c.us = ms * 1e3f;
       if (ms < cands[bi].us * 1e-3f) { cands.push_back(c); bi = (int)cands.size() - 1; }
     }
@@ -977,8 +1019,11 @@ static bool autotune(const void* x, void* y, int64_t n_faces, int C, const CubeP
   return run_cfg(*best, x, y, n_faces, C, g, st) == CP360_OK;
 }
 
+// Implicit first-call tuning is OPT-IN (CP360_AUTOTUNE=1): it allocates a flush buffer and synchronises on its
+// own events, which a call documented as asynchronous and allocation-free must not do by default. The default
+// path consults the built-in table (cubepad_tuned.h) and the results of explicit cp360_cubepad_autotune calls.
 static bool autotune_allowed(int64_t n_faces, int C, const CubePadGeom& g, cudaStream_t st) {
-  if (!env_int("CP360_AUTOTUNE", 1)) return false;
+  if (!env_int("CP360_AUTOTUNE", 0)) return false;
   const int64_t bytes = n_faces * C * ((int64_t)g.H * g.W + (int64_t)g.Ho * g.Wo) * 4;
   if (bytes < (int64_t)env_int("CP360_AUTOTUNE_MIN_MB", 16) << 20) return false;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1036,12 +1081,39 @@ int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, in
   if (!make_geom(H, W, pl, pr, pt, pd, &g) || C < 0 || C > 0x7fffffff) return CP360_OK;
   TuneCfg c;
   if (!tuned_lookup(tune_key(g, n_faces, (int)C), &c)) return CP360_OK;
+  char src[48];
+  if (c.from_table) snprintf(src, sizeof(src), "table@%d frames", c.from_table);
+  else snprintf(src, sizeof(src), "autotuned");
   if (c.algo == ALGO_ROW)
-    snprintf(buf, (size_t)buf_len, "row rb=%d tile_kb=%d order=%d slots=%d (%.1f us)", c.row_rb, c.row_tile_kb,
-             c.row_order1 - 1, c.row_slots, c.us);
+    snprintf(buf, (size_t)buf_len, "row rb=%d tile_kb=%d order=%d slots=%d (%.1f us, %s)", c.row_rb, c.row_tile_kb,
+             c.row_order1 - 1, c.row_slots, c.us, src);
   else
-    snprintf(buf, (size_t)buf_len, "cube stage_kb=%d stages=%d warps=%d (%.1f us)", c.cube_stage_kb, c.cube_stages,
-             c.cube_warps, c.us);
+    snprintf(buf, (size_t)buf_len, "cube stage_kb=%d stages=%d warps=%d (%.1f us, %s)", c.cube_stage_kb, c.cube_stages,
+             c.cube_warps, c.us, src);
+  return CP360_OK;
+}
+
+int cp360_cubepad_autotune(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl, int pr,
+                           int pt, int pd, int effort, void* stream) {
+  CubePadGeom g;
+  int rc = validate(x, y, n_faces, C, H, W, pl, pr, pt, pd, &g);
+  if (rc != CP360_OK) return rc;
+  CP360_CHECK_ARG(n_faces > 0 && C > 0, CP360_ERR_BAD_ARG, "nothing to tune");
+  CP360_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, CP360_ERR_ALIGN,
+                  "tuning applies to the 16 B-aligned fp32 path");
+  rc = require_device();
+  if (rc != CP360_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  CP360_CUDA_OK(cudaStreamIsCapturing(st, &cs));
+  CP360_CHECK_ARG(cs == cudaStreamCaptureStatusNone, CP360_ERR_BAD_ARG, "cannot tune while the stream is capturing");
+  TuneCfg cfg;
+  if (!autotune(x, y, n_faces, (int)C, g, st, &cfg, std::max(1, std::min(effort, 8)))) {
+    // fewer than two candidate tilings (or no scratch memory): nothing to choose, y holds the plain result
+    return cp360_cubepad_fwd_algo(x, y, n_faces, C, H, W, pl, pr, pt, pd, 4, ALGO_AUTO, stream);
+  }
+  std::lock_guard<std::mutex> lock(g_tuned_mutex);
+  g_tuned[tune_key(g, n_faces, (int)C)] = cfg;
   return CP360_OK;
 }
 

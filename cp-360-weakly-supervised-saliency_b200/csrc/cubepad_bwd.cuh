@@ -120,13 +120,15 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      uint32_t ticket = a.work ? atomicAdd(a.work, 1u) : 0u;   // drawn one step ahead of its use
+      // dynamic dealing: the first chunk of a CTA is its own index (no round trip to the counter in front of
+      // the first load), every further one gridDim.x + a ticket drawn one step ahead of its use
+      uint32_t ticket = blockIdx.x;
       for (int64_t it = 0;; ++it) {
         if (it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
         int64_t q = (int64_t)blockIdx.x + it * gridDim.x;
         if (a.work) {
           q = (int64_t)ticket;
-          if (q < a.n_chunks) ticket = atomicAdd(a.work, 1u);
+          if (q < a.n_chunks) ticket = gridDim.x + atomicAdd(a.work, 1u);
         }
         if (q >= a.n_chunks) {
           chunk_of[s] = -1;

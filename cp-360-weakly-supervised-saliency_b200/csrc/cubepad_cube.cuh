@@ -41,6 +41,7 @@ struct Cube2Args {
   int32_t stages;
   int32_t stage_words;  // 6 * kmax * H * W
   int32_t lut_off;      // byte offset of the position table in dynamic shared memory
+  int32_t epi_off;      // EPI kernels: byte offset of the per-stage {scale[kmax], shift[kmax]} slots
   int32_t ring_off;     // byte offset of the input ring
 };
 
@@ -56,6 +57,7 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   int64_t* chunk_of = reinterpret_cast<int64_t*>(empty + kCubeMaxStages); // [stages] chunk id staged there, -1: end
   uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + a.lut_off);      // [6*Ho*Wo]
   const uint32_t* ring = reinterpret_cast<const uint32_t*>(smem_raw + a.ring_off);
+  float* epi_s = reinterpret_cast<float*>(smem_raw + a.epi_off);          // [stages][2][kmax] (EPI kernels)
   const int HW = TH ? TH * TH : g.H * g.W;
   const int HoWo = TH ? (TH + 2 * TP) * (TH + 2 * TP) : g.Ho * g.Wo;
   const int n_pos = 6 * HoWo;
@@ -91,27 +93,50 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   CP360_TRACE_T0(1);
 
   if (warp == 0) {
-    // ---------------- producer: draw chunks, stage them `stages` deep
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t ticket = a.work ? atomicAdd(a.work, 1u) : 0u;   // drawn one step ahead of its use
-      for (int64_t it = 0;; ++it) {
+    // ---------------- producer: draw chunks, stage them `stages` deep. Plain copy: one lane does everything.
+    // EPI kernels: the whole warp walks the loop — lane 0 waits / draws / issues the bulk loads, all lanes copy
+    // the chunk's scale[] / shift[] slice into the stage's shared-memory slot, so the consumers never touch
+    // global memory for the epilogue constants.
+    if (!EPI && lane != 0) return;
+    int s = 0;
+    uint32_t ph = 0;
+    // dynamic dealing: the first chunk of a CTA is its own index (no round trip to the counter in front of
+    // the first load), every further one gridDim.x + a ticket drawn one step ahead of its use
+    uint32_t ticket = blockIdx.x;
+    for (int64_t it = 0;; ++it) {
+      int64_t q = 0;
+      if (lane == 0) {
         if (it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
-        int64_t q = (int64_t)blockIdx.x + it * gridDim.x;
+        q = (int64_t)blockIdx.x + it * gridDim.x;
         if (a.work) {
           q = (int64_t)ticket;
-          if (q < a.n_chunks) ticket = atomicAdd(a.work, 1u);
+          if (q < a.n_chunks) ticket = gridDim.x + atomicAdd(a.work, 1u);
         }
-        if (q >= a.n_chunks) {
+      }
+      if (EPI) {
+        __syncwarp();                                  // lane 0's acquire of empty[s] orders the slot writes below
+        q = __shfl_sync(0xffffffffu, q, 0);
+      }
+      if (q >= a.n_chunks) {
+        if (lane == 0) {
           chunk_of[s] = -1;
           tma::mbar_arrive(&full[s]);                  // completes the phase: consumers see the end mark
-          break;
         }
+        break;
+      }
+      const int64_t n = q / a.cblocks;
+      const int c0 = (int)(q - n * a.cblocks) * kmax;
+      const int kl = min(kmax, a.C - c0);
+      if (EPI) {
+        float* es = epi_s + (size_t)s * 2 * kmax;
+        for (int i = lane; i < kl; i += 32) {
+          es[i] = a.scale ? __ldg(a.scale + c0 + i) : 1.0f;
+          es[kmax + i] = a.shift ? __ldg(a.shift + c0 + i) : 0.0f;
+        }
+        __syncwarp();                                  // ... and the slot writes precede lane 0's release on full[s]
+      }
+      if (lane == 0) {
         chunk_of[s] = q;
-        const int64_t n = q / a.cblocks;
-        const int c0 = (int)(q - n * a.cblocks) * kmax;
-        const int kl = min(kmax, a.C - c0);
         const uint32_t bytes = (uint32_t)(kl * HW) * 4u;
         tma::mbar_expect_tx(&full[s], 6u * bytes);
         uint32_t* dst = const_cast<uint32_t*>(ring) + (size_t)s * a.stage_words;
@@ -119,13 +144,13 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
 #pragma unroll
         for (int f = 0; f < 6; ++f)
           tma::bulk_load(dst + f * fstride, src + (int64_t)f * a.C * HW, bytes, &full[s]);
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
-      if (a.work && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {   // last CTA: hand the pair back zeroed
-        a.work[0] = 0;
-        a.work[1] = 0;
-        __threadfence();
-      }
+      if (++s == a.stages) { s = 0; ph ^= 1u; }
+    }
+    if (lane == 0 && a.work && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {   // last CTA: hand the pair back zeroed
+      a.work[0] = 0;
+      a.work[1] = 0;
+      __threadfence();
     }
     return;
   }
@@ -147,13 +172,36 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
     const int kl = min(kmax, a.C - c0);
     const uint32_t* in_s = ring + (size_t)s * a.stage_words;
     uint32_t* __restrict__ out = a.y + ((n * 6) * a.out_C + a.out_coff + c0) * HoWo;
-    const float* sc_p = (EPI && a.scale) ? a.scale + c0 : nullptr;       // L1-resident after the first position
-    const float* sh_p = (EPI && a.shift) ? a.shift + c0 : nullptr;
+    const float* es = epi_s + (size_t)s * 2 * kmax;                       // this stage's scale[] / shift[] (EPI)
     auto epi = [&](uint32_t v, int cc) -> uint32_t {
-      Epi ep = {sc_p ? __ldg(sc_p + cc) : 1.0f, sh_p ? __ldg(sh_p + cc) : 0.0f, a.relu};
+      Epi ep = {es[cc], es[kmax + cc], a.relu};
       return epi_apply<EPI>(v, ep);
     };
-    if (TK > 0 && kl == TK) {
+    if (EPI && TK > 0 && kl == TK) {
+      // full chunk with an epilogue: a batch of channels' constants lives in registers while the thread walks
+      // all of its positions, so the epilogue costs three ALU instructions per word and no extra loads
+      constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
+#pragma unroll 1
+      for (int c8 = 0; c8 < TK; c8 += KB) {
+        float sc[KB], sh[KB];
+#pragma unroll
+        for (int j = 0; j < KB; ++j) { sc[j] = es[c8 + j]; sh[j] = es[kmax + c8 + j]; }
+#pragma unroll 1
+        for (int e = ctid; e < n_pos; e += n_cons) {
+          const uint32_t l = lut[e];
+          const uint32_t* sp = in_s + (l & 0xffffu) + c8 * HW;
+          uint32_t* __restrict__ dp = out + (int64_t)(l >> 29) * CHoWo + ((l >> 16) & 0x1fffu) + c8 * HoWo;
+          uint32_t v[KB];
+#pragma unroll
+          for (int j = 0; j < KB; ++j) v[j] = sp[j * HW];
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            const Epi ep = {sc[j], sh[j], a.relu};
+            __stcs(dp + j * HoWo, epi_apply<true>(v[j], ep));
+          }
+        }
+      }
+    } else if (TK > 0 && kl == TK) {
       // full chunk: channel walk unrolled in batches of 8, strides are immediates when TH > 0
       constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
 #pragma unroll 1

@@ -318,6 +318,13 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     if (a.nb > 1) { ya = band_i * a.Rb; yb = min(ya + a.Rb, H); np = 1; }
     else { ya = 0; yb = H; np = min(a.k, a.n_planes - plane0); }
     const uint32_t* in_s = ring + s * a.slot_words + (int)(((int64_t)plane0 * HW + ya * W) & 3);
+    // epilogue constants of the tile's first plane: fetched BEFORE the wait, so the global-load latency hides
+    // behind the bulk copy instead of stalling the first store of every tile
+    Epi ep0 = {1.0f, 0.0f, a.relu};
+    if (EPI) {
+      if (a.scale) ep0.sc = __ldg(a.scale + c);
+      if (a.shift) ep0.sh = __ldg(a.shift + c);
+    }
     tma::mbar_wait(&bar[s], phase);
 #ifdef CP360_TRACE
     if (lane == 0 && first_tile) CP360_TRACE_MIN(2);
@@ -327,8 +334,8 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
     for (int j = 0; j < np; ++j) {
       const uint32_t* band = in_s + j * HW;                           // row ya of this plane
       uint32_t* __restrict__ outp = a.y + ((int64_t)nf * a.out_C + a.out_coff + c) * HoWo;
-      Epi ep = {1.0f, 0.0f, a.relu};
-      if (EPI) {
+      Epi ep = ep0;
+      if (EPI && j > 0) {                                  // further planes of a multi-plane tile
         if (a.scale) ep.sc = __ldg(a.scale + c);
         if (a.shift) ep.sh = __ldg(a.shift + c);
       }

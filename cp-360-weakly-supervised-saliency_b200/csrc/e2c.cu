@@ -30,6 +30,25 @@ struct WithPad { static constexpr bool kPad = true; CubePadGeom g; };
 
 struct E2cPix { int f, map_idx, out_pix, out_plane; };
 
+// One map entry. Frames up to 2047 x 1023 use the packed word x0:11 | y0:10 | fx:5 | fy:5; larger frames
+// (4K / 8K equirects) the wide form of two words per pixel, x0:16 | y0:16 and fx:5 | fy:5, read as one
+// 8-byte load (cp360_e2c_build_map writes whichever form the frame size selects, cp360_e2c_map_words).
+struct MapEntry { int x0, y0; float fx, fy; };
+
+__device__ __forceinline__ MapEntry load_map(const uint32_t* __restrict__ packed, int idx, int Hin, int Win) {
+  MapEntry m;
+  if (Win > 2047 || Hin > 1023) {                      // uniform across the grid
+    const uint2 p = __ldg(reinterpret_cast<const uint2*>(packed) + idx);
+    m.x0 = (int)(p.x >> 16); m.y0 = (int)(p.x & 0xffffu);
+    m.fx = (float)((p.y >> 5) & 31u) * 0.03125f; m.fy = (float)(p.y & 31u) * 0.03125f;
+  } else {
+    const uint32_t p = __ldg(packed + idx);
+    m.x0 = (int)(p >> 20); m.y0 = (int)((p >> 10) & 1023u);
+    m.fx = (float)((p >> 5) & 31u) * 0.03125f; m.fy = (float)(p & 31u) * 0.03125f;
+  }
+  return m;
+}
+
 template <class GEOM>
 __device__ __forceinline__ bool e2c_locate(const GEOM& geom, int w, E2cPix* q) {
   const int ox = blockIdx.x * kE2cTileX + threadIdx.x;
@@ -72,9 +91,9 @@ e2c_kernel(const float* __restrict__ frames, const uint32_t* __restrict__ packed
   E2cPix q;
   if (!e2c_locate(geom, w, &q)) return;
   const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
-  const uint32_t p = __ldg(packed + q.map_idx);
-  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
-  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const MapEntry me = load_map(packed, q.map_idx, Hin, Win);
+  const int x0 = me.x0, y0 = me.y0;
+  const float fx = me.fx, fy = me.fy;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
   const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;   // BORDER_CONSTANT 0
@@ -137,9 +156,9 @@ e2c_kernel_c3v(const float* __restrict__ frames, const uint32_t* __restrict__ pa
   E2cPix q;
   if (!e2c_locate(geom, w, &q)) return;
   const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
-  const uint32_t p = __ldg(packed + q.map_idx);
-  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
-  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const MapEntry me = load_map(packed, q.map_idx, Hin, Win);
+  const int x0 = me.x0, y0 = me.y0;
+  const float fx = me.fx, fy = me.fy;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
   const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;   // BORDER_CONSTANT 0
@@ -216,9 +235,9 @@ e2c_kernel_anyc(const float* __restrict__ frames, const uint32_t* __restrict__ p
   E2cPix q;
   if (!e2c_locate(geom, w, &q)) return;
   const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
-  const uint32_t p = __ldg(packed + q.map_idx);
-  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
-  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const MapEntry me = load_map(packed, q.map_idx, Hin, Win);
+  const int x0 = me.x0, y0 = me.y0;
+  const float fx = me.fx, fy = me.fy;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
   const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;
@@ -263,9 +282,9 @@ e2c_kernel_u8c3(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
   E2cPix q;
   if (!e2c_locate(geom, w, &q)) return;
   const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
-  const uint32_t p = __ldg(packed + q.map_idx);
-  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
-  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const MapEntry me = load_map(packed, q.map_idx, Hin, Win);
+  const int x0 = me.x0, y0 = me.y0;
+  const float fx = me.fx, fy = me.fy;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
   const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;   // BORDER_CONSTANT 0
@@ -327,9 +346,9 @@ e2c_kernel_u8_anyc(const uint8_t* __restrict__ frames, const uint32_t* __restric
   E2cPix q;
   if (!e2c_locate(geom, w, &q)) return;
   const int f = q.f, ww = q.out_plane, pix = q.out_pix;     // output plane size / pixel (padded or not)
-  const uint32_t p = __ldg(packed + q.map_idx);
-  const int x0 = (int)(p >> 20), y0 = (int)((p >> 10) & 1023u);
-  const float fx = (float)((p >> 5) & 31u) * 0.03125f, fy = (float)(p & 31u) * 0.03125f;
+  const MapEntry me = load_map(packed, q.map_idx, Hin, Win);
+  const int x0 = me.x0, y0 = me.y0;
+  const float fx = me.fx, fy = me.fy;
   const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
   const bool x1_ok = x0 + 1 < Win, y1_ok = y0 + 1 < Hin;
@@ -441,7 +460,7 @@ static int e2c_prepare(E2cArgs* a, const float* mean_host, const float* std_host
   CP360_CHECK_ARG(a->B >= 0 && a->C >= 0 && a->w > 0 && a->Hin > 0 && a->Win > 0, CP360_ERR_BAD_ARG, "bad size");
   CP360_CHECK_ARG(a->Hin * 2 == a->Win, CP360_ERR_SHAPE,
                   "input must be 2:1 equirectangular (got %dx%d)", a->Win, a->Hin);
-  CP360_CHECK_ARG(a->Win <= 2047 && a->Hin <= 1023, CP360_ERR_RANGE, "packed map supports up to 2047x1023");
+  CP360_CHECK_ARG(a->Win <= 65535 && a->Hin <= 32767, CP360_ERR_RANGE, "frames larger than 65535 x 32767 are not supported");
   CP360_CHECK_ARG(a->layout == CP360_LAYOUT_NCHW || a->layout == CP360_LAYOUT_NHWC,
                   CP360_ERR_BAD_ARG, "unknown layout %d", a->layout);
   CP360_CHECK_ARG(!a->u8 || a->denom > 0.0f, CP360_ERR_BAD_ARG, "denom must be positive");
@@ -454,8 +473,10 @@ static int e2c_prepare(E2cArgs* a, const float* mean_host, const float* std_host
                     "fused normalisation needs mean and std and C in {1,3,4}");
   if (a->B == 0 || a->C == 0) return CP360_OK;
   CP360_CHECK_ARG(a->frames && a->packed && a->out, CP360_ERR_BAD_ARG, "null pointer");
+  const bool wide = a->Win > 2047 || a->Hin > 1023;
   CP360_CHECK_ARG((a->u8 || ((uintptr_t)a->frames % 4) == 0) && ((uintptr_t)a->out % 4) == 0 &&
-                      ((uintptr_t)a->packed % 4) == 0, CP360_ERR_ALIGN, "pointer not 4 B aligned");
+                      ((uintptr_t)a->packed % (wide ? 8 : 4)) == 0, CP360_ERR_ALIGN,
+                  "pointer not aligned (frames / faces 4 B, map %d B)", wide ? 8 : 4);
   int rc = require_device();
   if (rc != CP360_OK) return rc;
   a->nrm = NormParams{};

@@ -67,6 +67,11 @@ inline int32_t cv_round_f32_times32(double v) {
 
 extern "C" {
 
+int64_t cp360_e2c_map_words(int w, int Hin, int Win) {
+  if (w <= 0) return 0;
+  return (int64_t)6 * w * w * ((Win > 2047 || Hin > 1023) ? 2 : 1);
+}
+
 int cp360_e2c_build_map(int w, int Hin, int Win, double vfov_deg, uint32_t* packed_host,
                         int32_t* sx_host, int32_t* sy_host, double* inx_host, double* iny_host) {
   if (w <= 0 || Hin <= 1 || Win <= 1) { set_error("e2c map: non-positive size"); return CP360_ERR_BAD_ARG; }
@@ -74,10 +79,11 @@ int cp360_e2c_build_map(int w, int Hin, int Win, double vfov_deg, uint32_t* pack
     set_error("e2c map: input must be 2:1 equirectangular (got %dx%d)", Win, Hin);
     return CP360_ERR_SHAPE;
   }
-  if (packed_host && (Win > 2047 || Hin > 1023)) {
-    set_error("e2c packed map supports Win<=2047, Hin<=1023 (got %dx%d)", Win, Hin);
+  if (Win > 65535 || Hin > 32767) {
+    set_error("e2c map: frames larger than 65535 x 32767 are not supported (got %dx%d)", Win, Hin);
     return CP360_ERR_RANGE;
   }
+  const bool wide = Win > 2047 || Hin > 1023;          // two words per pixel (cp360_e2c_map_words)
   const double pi = M_PI;
   const double vfov = vfov_deg * pi / 180;
   const int views_deg[6][3] = {{180, 0, 0}, {0, -90, 0}, {0, 0, 0}, {-90, 0, 0}, {90, 0, 0}, {0, 90, 0}};
@@ -138,7 +144,12 @@ int cp360_e2c_build_map(int w, int Hin, int Win, double vfov_deg, uint32_t* pack
         if (sy_host) sy_host[o] = sy;
         if (packed_host) {
           const uint32_t x0 = (uint32_t)(sx >> 5), y0 = (uint32_t)(sy >> 5);
-          packed_host[o] = (x0 << 20) | (y0 << 10) | ((uint32_t)(sx & 31) << 5) | (uint32_t)(sy & 31);
+          if (wide) {
+            packed_host[2 * o] = (x0 << 16) | y0;
+            packed_host[2 * o + 1] = ((uint32_t)(sx & 31) << 5) | (uint32_t)(sy & 31);
+          } else {
+            packed_host[o] = (x0 << 20) | (y0 << 10) | ((uint32_t)(sx & 31) << 5) | (uint32_t)(sy & 31);
+          }
         }
       }
   }

@@ -71,6 +71,29 @@ def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
 
 
+def autotune_cubepad(x, lrtd_pad, effort=1):
+    """EXPLICIT tuning of one CubePad problem (cp360_cubepad_autotune): times candidate tilings on `x`, remembers the
+    winner for later calls with the same shape on this device, returns (padded tensor, description of the choice).
+    Allocates a flush buffer and synchronises — call it once per shape at start-up, never inside a CUDA graph
+    capture. Shapes of the cubic ResNet-50 / ConvLSTM are already covered by the built-in table."""
+    import ctypes
+    _require_cuda(x, "autotune_cubepad")
+    if x.dim() != 4 or x.dtype != torch.float32:
+        raise ValueError("autotune_cubepad expects a float32 [6N, C, H, W] tensor")
+    pads = get_pad_size(lrtd_pad)
+    p_l, p_r, p_t, p_d = pads
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty((n, c, h + p_t + p_d, w + p_l + p_r), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().cp360_cubepad_autotune(x.data_ptr(), y.data_ptr(), n, c, h, w, p_l, p_r, p_t, p_d,
+                                                     int(effort), st))
+        buf = ctypes.create_string_buffer(256)
+        _lib.check(_lib.lib().cp360_cubepad_tune_info(n, c, h, w, p_l, p_r, p_t, p_d, buf, 256))
+    return y, buf.value.decode()
+
+
 def cubepad_fused(x, pads, scale=None, shift=None, relu=False, out=None, out_channel_offset=0):
     """CubePad(act(x * scale[c] + shift[c])) in ONE pass (fp32): the eval-mode BatchNorm affine and
     ReLU that precede CubePad in the cubic ResNet (model/resnet_cubic.py:89-92) never cost a tensor

@@ -23,7 +23,8 @@ class Equi2Cube:
         self.vfov = vfov
         w = self.output_width
         n = 6 * w * w
-        self.packed = np.empty(n, dtype=np.uint32)
+        # one uint32 per output pixel, two for frames beyond 2047 x 1023 (cp360.h: cp360_e2c_build_map)
+        self.packed = np.empty(int(_lib.lib().cp360_e2c_map_words(w, self.input_height, self.input_width)), dtype=np.uint32)
         self.sx = np.empty(n, dtype=np.int32)
         self.sy = np.empty(n, dtype=np.int32)
         inx = np.empty(n, dtype=np.float64)

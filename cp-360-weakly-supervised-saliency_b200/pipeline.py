@@ -127,17 +127,28 @@ class SphericalPipeline:
         self._lib = _lib.lib()
 
     # ---------------------------------------------------------------- accounting
+    def _e2c_touched(self):
+        sx, sy = self.e2c.sx.astype(np.int64).reshape(-1), self.e2c.sy.astype(np.int64).reshape(-1)
+        x0, y0, fx, fy = sx >> 5, sy >> 5, sx & 31, sy & 31
+        W = self.equi_w
+        t = [y0 * W + x0, (y0 * W + x0 + 1)[fx > 0], ((y0 + 1) * W + x0)[fy > 0],
+             ((y0 + 1) * W + x0 + 1)[(fx > 0) & (fy > 0)]]
+        return np.unique(np.concatenate(t))
+
     def e2c_bytes_per_frame(self):
         """Algorithmic bytes of K1: unique input pixels touched * C * 4 + faces written."""
+        if getattr(self, "_e2c_bytes", None) is None:
+            w = self.cube
+            self._e2c_bytes = int(self._e2c_touched().size) * 3 * 4 + 6 * w * w * 3 * 4
+        return self._e2c_bytes
+
+    def e2c_sector_bytes_per_frame(self, elem=4):
+        """What DRAM must deliver at its 32 B access granularity: every sector holding a touched pixel once,
+        plus the faces written — the physical floor of a gather that cannot fetch less than a sector."""
+        px = self._e2c_touched() * 3 * elem                       # byte offset of each touched pixel (3 channels)
+        sectors = np.unique(np.concatenate([px // 32, (px + 3 * elem - 1) // 32]))
         w = self.cube
-        p = self.e2c.packed.astype(np.int64)
-        x0, y0 = p >> 20, (p >> 10) & 1023
-        fx, fy = (p >> 5) & 31, p & 31
-        W = self.equi_w
-        touched = [y0 * W + x0, (y0 * W + x0 + 1)[fx > 0], ((y0 + 1) * W + x0)[fy > 0],
-                   ((y0 + 1) * W + x0 + 1)[(fx > 0) & (fy > 0)]]
-        n = np.unique(np.concatenate([t.reshape(-1) for t in touched])).size
-        return int(n) * 3 * 4 + 6 * w * w * 3 * 4
+        return int(sectors.size) * 32 + 6 * w * w * 3 * 4
 
     def cubepad_bytes_per_frame(self, site):
         C, H, p = site
@@ -150,6 +161,28 @@ class SphericalPipeline:
     def bytes_per_frame(self):
         return (self.e2c_bytes_per_frame() + sum(self.cubepad_bytes_per_frame(s) for s in self.sites) +
                 self.c2e_max_bytes_per_frame())
+
+    def fused_bytes_per_frame(self):
+        """(algorithmic bytes of the fused chain, bytes the UNFUSED network moves for the same tensors).
+
+        Fused chain (step_fused): e2c + CubePad(3) in one kernel (the faces are never written), BN-affine + ReLU
+        folded into the pad at the 17 ResNet sites, the ConvLSTM site written from its two cat sources.
+        The unfused network pays for the same results: e2c + pad (faces written, then read), a BN+ReLU pass of
+        its own per site (read x, write x': resnet_cubic.py:89-92) before the pad reads x', and a torch.cat pass
+        (read both sources, write the cat: clstm.py:57) before the pad reads the cat."""
+        w, p0 = self.cube, self.sites[0][2]
+        faces = 6 * w * w * 3 * 4
+        touched = self.e2c_bytes_per_frame() - faces
+        padded0 = 6 * 3 * (w + 2 * p0) ** 2 * 4
+        fused = touched + padded0
+        unfused = touched + faces + faces + padded0
+        for (C, H, p) in self.sites[1:]:
+            x, y = 6 * C * H * H * 4, 6 * C * (H + 2 * p) ** 2 * 4
+            fused += x + y
+            unfused += 3 * x + y
+        fused += self.c2e_max_bytes_per_frame()
+        unfused += self.c2e_max_bytes_per_frame()
+        return fused, unfused
 
     # ---------------------------------------------------------------- buffers
     def allocate(self, B):
@@ -169,6 +202,15 @@ class SphericalPipeline:
         self.sal = torch.empty((self.B, 2 * fw, 4 * fw), dtype=torch.float32, device=dev)
         self._packed = self.e2c._map_on(dev)
         self._taps, self._wts = self.c2e._plan_on(dev)
+        # fused chain (step_fused): folded eval-mode BatchNorm parameters per ResNet site, and the ConvLSTM
+        # site's input as the two tensors the reference concatenates (input_, h_cur: clstm.py:57)
+        self.bn_scale, self.bn_shift = [None], [None]
+        for (C, H, p) in self.sites[1:-1]:
+            self.bn_scale.append(torch.rand(C, dtype=torch.float32, device=dev, generator=g) + 0.5)
+            self.bn_shift.append(torch.randn(C, dtype=torch.float32, device=dev, generator=g))
+        Cf, Hf, _ = self.sites[-1]
+        half = Cf // 2
+        self.cat_src = [self.site_in[-1][:, :half].contiguous(), self.site_in[-1][:, half:].contiguous()]
         return self
 
     def synthetic_frames(self, B, generator=None):
@@ -220,14 +262,61 @@ class SphericalPipeline:
             on_launch("end", -1)
         return self.sal
 
-    def capture(self, frames):
+    def step_fused(self, frames, on_launch=None):
+        """The same chain with every producer-side fusion the library offers (north_star's
+        "fused into the producer of the conv input so no separate pad copy exists"):
+          cp360_e2c_cubepad_fwd            frames -> CubePad(3)(faces), the faces are never written
+          cp360_cubepad_fused_fwd x 17     CubePad(relu(x * scale[c] + shift[c])) — BN + ReLU + pad in one pass
+          cp360_cubepad_fused_fwd x 2      the ConvLSTM site as CubePad(cat(a, b)) written one source at a time
+          cp360_c2e_max_fwd                back-projection + channel max
+        Site outputs equal CubePad applied to the affine+ReLU'd / concatenated inputs bit for bit
+        (tests/test_gpu_parity.py::test_pipeline_fused_chain_matches_unfused_ops)."""
+        if frames.shape[0] != self.B:
+            self.allocate(frames.shape[0])
+        lib, chk = self._lib, _lib.check
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        n = 6 * self.B
+        if on_launch:
+            on_launch("e2c_cubepad", 0)
+        p = self.sites[0][2]
+        chk(lib.cp360_e2c_cubepad_fwd(frames.data_ptr(), int(frames.dtype == torch.uint8), self._packed.data_ptr(),
+                                      self.site_out[0].data_ptr(), self.B, self.equi_h, self.equi_w, 3, self.cube,
+                                      p, p, p, p, 255.0, None, None, st))
+        last = len(self.sites) - 1
+        for i, (C, H, p) in enumerate(self.sites):
+            if i == 0:
+                continue
+            if i < last:
+                if on_launch:
+                    on_launch("cubepad_bn_relu", i)
+                chk(lib.cp360_cubepad_fused_fwd(self.site_in[i].data_ptr(), self.site_out[i].data_ptr(), n, C, H, H,
+                                                p, p, p, p, self.bn_scale[i].data_ptr(), self.bn_shift[i].data_ptr(),
+                                                1, 0, 0, st))
+            else:
+                off = 0
+                for src in self.cat_src:
+                    if on_launch:
+                        on_launch("cubepad_cat", i)
+                    chk(lib.cp360_cubepad_fused_fwd(src.data_ptr(), self.site_out[i].data_ptr(), n, src.shape[1], H, H,
+                                                    p, p, p, p, None, None, 0, C, off, st))
+                    off += src.shape[1]
+        if on_launch:
+            on_launch("c2e_max", -1)
+        chk(lib.cp360_c2e_max_fwd(self.cam.data_ptr(), self._taps.data_ptr(), self._wts.data_ptr(),
+                                  self.sal.data_ptr(), self.B, self.cam_channels, self.feat_w, st))
+        if on_launch:
+            on_launch("end", -1)
+        return self.sal
+
+    def capture(self, frames, fused=False):
         """Capture one step over `frames` (a fixed device buffer) in a CUDA graph; returns the
         graph (call .replay()). The first eager step doubles as warm-up (function attributes)."""
-        self.step(frames)
+        fn = self.step_fused if fused else self.step
+        fn(frames)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.step(frames)
+            fn(frames)
         return graph
 
     # ---------------------------------------------------------------- host-buffer entry point
@@ -242,34 +331,167 @@ class SphericalPipeline:
         torch.cuda.current_stream(self.device).synchronize()
         return out_host
 
-    def process_host(self, host_batches, out_host):
+    def process_host(self, host_batches, out_host, depth=3, copy_streams=1, fused=False):
         """Streamed end-to-end path: host_batches is a sequence of pinned [B,Hin,Win,3] host tensors
-        (uint8 video frames or float32), out_host a pinned [len(host_batches),B,2fw,4fw] tensor. Uploads run on a copy
-        stream into two alternating device buffers while the previous batch computes; every
-        batch's maps are copied back to the host. Returns after everything has landed."""
+        (uint8 video frames or float32), out_host a pinned [len(host_batches),B,2fw,4fw] tensor. Uploads run on
+        `copy_streams` copy streams (each batch split evenly between them) into a ring of `depth` device buffers,
+        up to depth-1 batches ahead of the chain; every batch's maps are copied back to the host on the compute
+        stream. Returns after everything has landed."""
         dev = self.device
         B = host_batches[0].shape[0]
         if B != self.B:
             self.allocate(B)
         dt = host_batches[0].dtype
-        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] != B or self._stage[0].dtype != dt:
-            self._stage = [torch.empty((B, self.equi_h, self.equi_w, 3), dtype=dt, device=dev) for _ in range(2)]
-            self._copy_stream = torch.cuda.Stream(device=dev)
+        depth, copy_streams = max(2, int(depth)), max(1, int(copy_streams))
+        st = getattr(self, "_stage", None)
+        if st is None or len(st) != depth or st[0].shape[0] != B or st[0].dtype != dt or len(self._copy_streams) != copy_streams:
+            self._stage = [torch.empty((B, self.equi_h, self.equi_w, 3), dtype=dt, device=dev) for _ in range(depth)]
+            self._copy_streams = [torch.cuda.Stream(device=dev) for _ in range(copy_streams)]
         compute = torch.cuda.current_stream(dev)
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [None, None]
-        self._copy_stream.wait_stream(compute)
+        freed = [None] * depth
+        part = (B + copy_streams - 1) // copy_streams
+        for cs in self._copy_streams:
+            cs.wait_stream(compute)
+        run = self.step_fused if fused else self.step
         for i, hb in enumerate(host_batches):
-            k = i & 1
-            with torch.cuda.stream(self._copy_stream):
-                if freed[k] is not None:
-                    self._copy_stream.wait_event(freed[k])
-                self._stage[k].copy_(hb, non_blocking=True)
-                copied[k].record(self._copy_stream)
-            compute.wait_event(copied[k])
-            sal = self.step(self._stage[k])
+            k = i % depth
+            for j, cs in enumerate(self._copy_streams):
+                with torch.cuda.stream(cs):
+                    if freed[k] is not None:
+                        cs.wait_event(freed[k])
+                    self._stage[k][j * part:(j + 1) * part].copy_(hb[j * part:(j + 1) * part], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                compute.wait_event(ev)
+            sal = run(self._stage[k])
             freed[k] = torch.cuda.Event()
             freed[k].record(compute)
             out_host[i].copy_(sal, non_blocking=True)
         compute.synchronize()
         return out_host
+
+    def h2d_probe(self, host_batches, repeats=1):
+        """Upload-only ceiling of process_host: the same pinned batches through the same staging ring and copy
+        streams, no kernels, no D2H. Returns GB/s (CUDA events on the compute stream)."""
+        dev = self.device
+        if getattr(self, "_stage", None) is None:
+            raise RuntimeError("call process_host once first (it owns the staging ring)")
+        compute = torch.cuda.current_stream(dev)
+        B = host_batches[0].shape[0]
+        part = (B + len(self._copy_streams) - 1) // len(self._copy_streams)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(compute)
+        for cs in self._copy_streams:
+            cs.wait_event(e0)
+        nbytes = 0
+        for _ in range(repeats):
+            for i, hb in enumerate(host_batches):
+                k = i % len(self._stage)
+                for j, cs in enumerate(self._copy_streams):
+                    with torch.cuda.stream(cs):
+                        self._stage[k][j * part:(j + 1) * part].copy_(hb[j * part:(j + 1) * part], non_blocking=True)
+                nbytes += hb.numel() * hb.element_size()
+        for cs in self._copy_streams:
+            compute.wait_stream(cs)
+        e1.record(compute)
+        compute.synchronize()
+        return nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+class TemporalCubePadSequence:
+    """The hot-path work of the ConvLSTM temporal model (BASELINE.json configs[3]) for B
+    windows at a time: per time step the three CubePads of one cell evaluation (model/clstm.py:57-64)
+
+        CubePad(cat(input_, h_cur))   [6B, feat+hid, w, w]   written from its two sources (cubepad_cat)
+        CubePad(relu(Conv1(.)))       [6B, 4*hid,   w, w]
+        CubePad(relu(Conv2(.)))       [6B, 4*hid,   w, w]
+
+    and, after `seq_len` steps, the back-projection + channel max of the hidden state
+    (temporal_model/test_temporal.py:82-84). Windows are independent — the state is reset for every output
+    frame (test_temporal.py:69-73) — so they batch along the cube dimension. The three convolutions and the gate
+    math are cuDNN's / PyTorch's business (out of scope): their outputs are device-resident stand-ins of the
+    exact shapes. feat = hid = 2048 on 8x8 faces is BASELINE's synthetic width; feat = hid = 1000 on 7x7
+    faces is what the reference runs (config.yaml:21-22)."""
+
+    def __init__(self, feat_channels=2048, hidden_channels=2048, feat_w=8, seq_len=5, device=None, seed=4321,
+                 align_corners=False, fused_cat=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("TemporalCubePadSequence needs a CUDA device (sm_100a); no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.feat, self.hid, self.w, self.seq_len = int(feat_channels), int(hidden_channels), int(feat_w), int(seq_len)
+        self.fused_cat = bool(fused_cat)
+        self.c2e = Cube2Equi(self.w, align_corners=align_corners)
+        self.seed = seed
+        self.B = 0
+        self._lib = _lib.lib()
+
+    def sites(self):
+        return [(self.feat + self.hid, self.w, 1), (4 * self.hid, self.w, 1), (4 * self.hid, self.w, 1)]
+
+    def bytes_per_frame(self):
+        """Algorithmic bytes per OUTPUT frame (= one window): seq_len x the three pads + one c2e+max."""
+        w = self.w
+        pads = sum(6 * C * (w * w + (w + 2) * (w + 2)) * 4 for C, _, _ in self.sites())
+        return self.seq_len * pads + 6 * self.hid * w * w * 4 + 8 * w * w * 4
+
+    def launches_per_window_batch(self):
+        return self.seq_len * (4 if self.fused_cat else 3) + 2      # + fill and c2e_max
+
+    def allocate(self, B):
+        dev, w = self.device, self.w
+        g = torch.Generator(device=dev).manual_seed(self.seed)
+        self.B = int(B)
+        n = 6 * self.B
+        r = lambda c: torch.randn((n, c, w, w), dtype=torch.float32, device=dev, generator=g)   # noqa: E731
+        # one set of stand-ins PER TIME STEP (as in the model, where every step's tensors are fresh conv outputs):
+        # nothing a step reads was touched by the previous step, so no input is served from L2 by accident
+        self.x = [r(self.feat) for _ in range(self.seq_len)]         # the window's feature frames
+        self.hs = [r(self.hid) for _ in range(self.seq_len + 1)]     # hidden state before each step / after the last
+        self.mid = [[r(4 * self.hid), r(4 * self.hid)] for _ in range(self.seq_len)]   # Conv1 / Conv2 outputs
+        self.h = self.hs[-1]
+        self.cat = torch.empty((n, self.feat + self.hid, w, w), dtype=torch.float32, device=dev) if not self.fused_cat else None
+        self.out_cat = torch.empty((n, self.feat + self.hid, w + 2, w + 2), dtype=torch.float32, device=dev)
+        self.out_mid = [torch.empty((n, 4 * self.hid, w + 2, w + 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.sal = torch.empty((self.B, 2 * w, 4 * w), dtype=torch.float32, device=dev)
+        self._taps, self._wts = self.c2e._plan_on(dev)
+        return self
+
+    def window_batch(self, on_launch=None):
+        """One batch of B windows: seq_len cell evaluations' CubePads, then c2e + max of the hidden state."""
+        lib, chk = self._lib, _lib.check
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        n, w = 6 * self.B, self.w
+        for t in range(self.seq_len):
+            if self.fused_cat:
+                off = 0
+                for src in (self.x[t], self.hs[t]):
+                    if on_launch:
+                        on_launch("cubepad_cat", 0)
+                    chk(lib.cp360_cubepad_fused_fwd(src.data_ptr(), self.out_cat.data_ptr(), n, src.shape[1], w, w,
+                                                    1, 1, 1, 1, None, None, 0, self.feat + self.hid, off, st))
+                    off += src.shape[1]
+            else:
+                torch.cat((self.x[t], self.hs[t]), 1, out=self.cat)
+                if on_launch:
+                    on_launch("cubepad", 0)
+                chk(lib.cp360_cubepad_fwd(self.cat.data_ptr(), self.out_cat.data_ptr(), n, self.feat + self.hid, w, w,
+                                          1, 1, 1, 1, 4, st))
+            for j in range(2):
+                if on_launch:
+                    on_launch("cubepad", 1 + j)
+                chk(lib.cp360_cubepad_fwd(self.mid[t][j].data_ptr(), self.out_mid[j].data_ptr(), n, 4 * self.hid, w, w,
+                                          1, 1, 1, 1, 4, st))
+        if on_launch:
+            on_launch("c2e_max", -1)
+        chk(lib.cp360_c2e_max_fwd(self.h.data_ptr(), self._taps.data_ptr(), self._wts.data_ptr(),
+                                  self.sal.data_ptr(), self.B, self.hid, w, st))
+        if on_launch:
+            on_launch("end", -1)
+        return self.sal
+
+    def capture(self):
+        self.window_batch()
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.window_batch()
+        return graph

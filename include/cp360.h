@@ -18,8 +18,9 @@
  *     allocates or frees caller memory and keeps no reference after the call returns.
  *   - every call returns a cp360_status (0 = ok). Kernels are launched asynchronously on
  *     `stream`; launch errors are reported, execution errors surface at the caller's next sync.
- *   - thread-safe for distinct streams; no global mutable state except a thread-local
- *     last-error string.
+ *   - thread-safe for distinct streams. Global state, all mutex- or atomic-guarded: a thread-local
+ *     last-error string, the launch counter, the per-device pool of work counters (common.cu), the
+ *     CubePad tiling table (cubepad.cu) and the registry of cp360_host_alloc buffers.
  *   - there is NO CPU fallback: without a CUDA device the *_fwd/_bwd calls return
  *     CP360_ERR_CUDA. The *_build_* calls are host-only (map construction, once per
  *     resolution) and work anywhere.
@@ -101,8 +102,19 @@ CP360_API int cp360_cubepad_fused_fwd(const float* x_dev, float* y_dev, int64_t 
                             int pl, int pr, int pt, int pd, const float* scale_dev, const float* shift_dev,
                             int relu, int64_t out_C, int64_t out_c_off, void* stream);
 
-/* Host: human-readable tiling the first-call autotuner chose for this problem on the current device
- * ("" if the problem has not been tuned: too small, stream was capturing, CP360_AUTOTUNE=0). */
+/* Device, fp32, EXPLICIT tuning — the one CubePad call that allocates and synchronises: times candidate tilings
+ * of this problem on the caller's tensors (y is written with the correct result by every candidate; a 160 MB
+ * flush buffer and two events are created and destroyed inside the call, which waits for its own launches)
+ * and remembers the winner for later cp360_cubepad_fwd calls with the same (device, geometry, C, n_faces).
+ * effort 1..8 scales the repetitions. Not allowed during stream capture. cp360_cubepad_fwd itself never tunes:
+ * it uses, in this order, a result of this call, the built-in table measured on B200 for the cubic-ResNet-50 /
+ * ConvLSTM shapes (csrc/cubepad_tuned.h), and shape heuristics. (CP360_AUTOTUNE=1 restores implicit
+ * first-call tuning for experiments.) */
+CP360_API int cp360_cubepad_autotune(const void* x_dev, void* y_dev, int64_t n_faces, int64_t C, int H, int W,
+                           int pl, int pr, int pt, int pd, int effort, void* stream);
+
+/* Host: human-readable tiling cp360_cubepad_fwd uses for this problem on the current device and where it
+ * came from ("" = shape heuristics: no autotune result and no table row for this site). */
 CP360_API int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,
                             char* buf, int buf_len);
 
@@ -130,10 +142,14 @@ CP360_API int cp360_cubepad_bwd_f32(const float* gy_dev, float* gx_dev, int64_t 
  * Replaces Equi2Cube.__init__, equi_to_cube.py:12-110 (float64, table-lookup inverse trig) and
  * the float32 cast + cv2 fixed-point conversion of :122-125 / cv2.remap.
  * Outputs (any may be NULL):
- *   packed_host[6*w*w] uint32  x0<<20 | y0<<10 | fx<<5 | fy  (x0 = sx>>5, fx = sx&31, ...)
+ *   packed_host[cp360_e2c_map_words(w,Hin,Win)] uint32 — the device map. Frames up to 2047 x 1023 (the
+ *     reference's 1920 x 960): one word per pixel, x0<<20 | y0<<10 | fx<<5 | fy (x0 = sx>>5, fx = sx&31, ...).
+ *     Larger frames (4K / 8K equirects): two words per pixel, x0<<16 | y0 then fx<<5 | fy; the device
+ *     copy must then be 8 B aligned. The *_fwd calls pick the form from Hin / Win the same way.
  *   sx_host, sy_host[6*w*w] int32   cvRound(float32(inX)*32), cvRound(float32(inY)*32)
  *   inx_host, iny_host[6*w*w] double  the reference's self.inXs / self.inYs (1-based coords)
- * Requires Win <= 2047 and Hin <= 1023 for the packed form (CP360_ERR_RANGE otherwise). */
+ * CP360_ERR_RANGE beyond 65535 x 32767. */
+CP360_API int64_t cp360_e2c_map_words(int w, int Hin, int Win);
 CP360_API int cp360_e2c_build_map(int w, int Hin, int Win, double vfov_deg, uint32_t* packed_host,
                         int32_t* sx_host, int32_t* sy_host, double* inx_host, double* iny_host);
 
@@ -252,6 +268,18 @@ CP360_API int cp360_npy_read_f32(const char* path, float* dst_host, int64_t n_el
 /* Write src_host as a float32 C-order .npy, byte-identical to numpy.save (format 1.0). Written to
  * a temporary file and renamed, so readers never see a partial file. */
 CP360_API int cp360_npy_write_f32(const char* path, const float* src_host, int ndim, const int64_t* shape);
+
+/* ------------------------------------------------------------------------------------------
+ * Host staging memory for the end-to-end path: the reference reads decoded video frames into host
+ * arrays (static_model/dataset_feat_extractor.py:119-142) and copies per frame (class_activation_model.py:58).
+ * Page-locked buffers let the copy engines stream them at PCIe speed.
+ * mode 0: cudaHostAlloc(portable); 1: + write-combined; 2: 2 MB-aligned anonymous mapping with
+ * MADV_HUGEPAGE, touched and cudaHostRegister'ed (fewer IOMMU translations per byte on multi-GPU hosts).
+ * These two calls are the only ones in the library that allocate; the memory belongs to the caller
+ * until cp360_host_free.
+ * ---------------------------------------------------------------------------------------- */
+CP360_API int cp360_host_alloc(uint64_t bytes, int mode, void** out_host);
+CP360_API int cp360_host_free(void* host_ptr);
 
 #ifdef __cplusplus
 }

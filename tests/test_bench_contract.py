@@ -30,8 +30,25 @@ def test_reference_arm_prints_one_json_line():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    # "reference" = the unmodified reference (live checkout or the sha256-pinned oracle/_ref staging copy), else the port
+    from oracle import ref_loader
+    want_kind = "reference" if ref_loader.available() and (ref_loader.kind() == "live" or ref_loader.verify()) else "port"
+    assert cb["kind"] == want_kind and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_runs_from_the_staged_copy(tmp_path):
+    """What the GPU box does: /root/reference is absent there, the arm must run the staged, verified copy."""
+    from oracle import ref_loader
+    if not ref_loader.verify():
+        pytest.skip("oracle/_ref not staged (run __graft_entry__.build() where /root/reference exists)")
+    env = dict(os.environ, CP360_REFERENCE=str(tmp_path / "absent"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-frames", "1", "--workload", "clstm", "--clstm-variant", "reference"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert line["cpu_baseline"]["kind"] == "reference" and "oracle/_ref" in line["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -95,21 +95,47 @@ def test_cubepad_vs_oracle(dev, shape, pad, algo):
 @pytest.mark.parametrize("shape,pad", [((12, 16, 64, 64), 1), ((6, 24, 32, 32), 1), ((12, 64, 16, 16), 1),
                                        ((6, 3, 128, 128), 3), ((6, 40, 28, 28), [1, 2, 2, 1])])
 def test_cubepad_autotuned_path(dev, shape, pad, monkeypatch):
-    """First AUTO call of a problem times candidate tilings on the caller's tensors and caches the
-    winner; the tuned launch (and every candidate it tried) must stay bit-exact."""
-    monkeypatch.setenv("CP360_AUTOTUNE_MIN_MB", "0")
+    """cp360_cubepad_autotune (explicit; cp360_cubepad_fwd itself never tunes) times candidate tilings on the
+    caller's tensors and remembers the winner; the tuned launch (and every candidate it tried) must stay bit-exact.
+    CP360_AUTOTUNE=1 restores implicit first-call tuning."""
     x = np.random.default_rng(zlib.crc32(repr(shape).encode())).standard_normal(shape).astype(np.float32)
     want = ocp.cubepad(x, pad)
     xt = torch.from_numpy(x).to(dev)
     pads = cp360_b200.get_pad_size(pad)
-    y1 = cp360_b200.cubepad_forward(xt, pads)           # tunes
-    buf = ctypes.create_string_buffer(256)
-    n, c, h, w_ = shape
-    _lib.check(_lib.lib().cp360_cubepad_tune_info(n, c, h, w_, pads[0], pads[1], pads[2], pads[3], buf, 256))
-    assert buf.value, "problem was not tuned"
-    y2 = cp360_b200.cubepad_forward(xt, pads)           # cached configuration
+    y1, info = cp360_b200.autotune_cubepad(xt, pad)
+    assert "autotuned" in info, "problem was not tuned: %r" % info
+    y2 = cp360_b200.cubepad_forward(xt, pads)           # remembered configuration
     np.testing.assert_array_equal(y1.cpu().numpy(), want)
     np.testing.assert_array_equal(y2.cpu().numpy(), want)
+    # implicit first-call tuning, opt-in
+    monkeypatch.setenv("CP360_AUTOTUNE", "1")
+    monkeypatch.setenv("CP360_AUTOTUNE_MIN_MB", "0")
+    x3 = torch.from_numpy(np.concatenate([x, x])).to(dev)          # another batch size: a new problem
+    y3 = cp360_b200.cubepad_forward(x3, pads)
+    buf = ctypes.create_string_buffer(256)
+    n, c, h, w_ = x3.shape
+    _lib.check(_lib.lib().cp360_cubepad_tune_info(n, c, h, w_, pads[0], pads[1], pads[2], pads[3], buf, 256))
+    assert b"autotuned" in buf.value
+    np.testing.assert_array_equal(y3.cpu().numpy(), np.concatenate([want, want]))
+
+
+def test_cubepad_builtin_table_covers_the_network_sites(dev):
+    """The tiling of every cubic-ResNet-50 / ConvLSTM site comes from the built-in table (csrc/cubepad_tuned.h,
+    measured on B200) without any tuning call: deterministic, allocation-free, usable under stream capture."""
+    lib = _lib.lib()
+    buf = ctypes.create_string_buffer(256)
+    missing = []
+    for cube in (256, 224):
+        for (C, H, p) in dict.fromkeys(cp360_b200.resnet50_cubepad_sites(cube) + [(2048, cube // 32, 1)]):
+            for frames in (1, 8, 32):
+                _lib.check(lib.cp360_cubepad_tune_info(6 * frames, C, H, H, p, p, p, p, buf, 256))
+                if b"table@" not in buf.value:
+                    missing.append((C, H, p, frames))
+    for (C, H) in ((2000, 7), (4000, 7), (4096, 8), (8192, 8)):
+        _lib.check(lib.cp360_cubepad_tune_info(96, C, H, H, 1, 1, 1, 1, buf, 256))
+        if b"table@" not in buf.value:
+            missing.append((C, H, 1, 16))
+    assert not missing, "sites without a table row: %s" % missing
 
 
 FUSED_SHAPES = [((6, 8, 16, 16), 1), ((12, 16, 8, 8), 1), ((6, 12, 7, 7), 1), ((6, 4, 32, 32), 1), ((12, 6, 64, 64), 1),
@@ -469,6 +495,28 @@ def test_e2c_float64_input_follows_dtype(dev):
     sx, sy = oe2c.fixed_maps(16, 64, 128)
     np.testing.assert_allclose(np.stack([faces[i] for i in range(6)]),
                                oe2c.to_cube(img.astype(np.float32), sx, sy), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_e2c_4k_frames_wide_map(dev, u8):
+    """3840 x 1920 equirects (beyond the 11 + 10 bit packed map): the wide two-word map format, float32 and uint8
+    frames, plain and fused-with-CubePad kernels — bit-exact against the oracle's cv2 restatement."""
+    rng = np.random.default_rng(44)
+    H, W, w, B = 1920, 3840, 48, 2
+    if u8:
+        frames8 = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+        frames = (frames8.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+    else:
+        frames = rng.random((B, H, W, 3), dtype=np.float32)
+    e2c = cp360_b200.Equi2Cube(w, frames[0])
+    sx, sy = oe2c.fixed_maps(w, H, W)
+    assert np.array_equal(e2c.sx.reshape(-1), sx.reshape(-1)) and (sx >> 5).max() > 2047
+    want = np.concatenate([oe2c.to_cube(frames[b], sx, sy) for b in range(B)]).transpose(0, 3, 1, 2)
+    src = torch.from_numpy(frames8 if u8 else frames).to(dev)
+    got = e2c.to_cube_tensor(src)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    padded = e2c.to_padded_cube_tensor(src, 3)
+    np.testing.assert_array_equal(padded.cpu().numpy(), ocp.cubepad(np.ascontiguousarray(want), 3))
 
 
 def test_e2c_full_size_properties(dev):

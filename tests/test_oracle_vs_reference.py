@@ -96,6 +96,31 @@ def test_e2c_maps_and_faces_live(ref, w, H, vfov):
     np.testing.assert_array_equal(got.reshape(want.shape), want)
 
 
+def test_e2c_4k_frame_maps_live(ref):
+    """Frames beyond 2047 x 1023 (the reference accepts any 2:1 frame, equi_to_cube.py:15): a 3840 x 1920 equirect
+    -> 64-px faces. Integer maps bit-exact against the reference object, and the wide device map (two words per
+    pixel, include/cp360.h) decodes to the same entries."""
+    e2c_mod = ref[1]
+    w, H, W = 64, 1920, 3840
+    img = np.zeros((H, W, 1), dtype=np.float32)
+    obj = e2c_mod.Equi2Cube(w, img)
+    ref_sx = np.stack([np.rint(a.astype(np.float32) * np.float32(32)).astype(np.int32).reshape(w, w) for a in obj.inXs])
+    ref_sy = np.stack([np.rint(a.astype(np.float32) * np.float32(32)).astype(np.int32).reshape(w, w) for a in obj.inYs])
+    mine = cp360_b200.Equi2Cube(w, img)
+    np.testing.assert_array_equal(mine.sx, ref_sx)
+    np.testing.assert_array_equal(mine.sy, ref_sy)
+    assert int(ref_sx.max()) >> 5 > 2047 and int(ref_sy.max()) >> 5 > 1023          # really needs the wide form
+    assert mine.packed.size == 2 * 6 * w * w == _lib.lib().cp360_e2c_map_words(w, H, W)
+    lo, hi = mine.packed[0::2].astype(np.int64), mine.packed[1::2].astype(np.int64)
+    np.testing.assert_array_equal((lo >> 16).reshape(6, w, w), ref_sx >> 5)
+    np.testing.assert_array_equal((lo & 0xffff).reshape(6, w, w), ref_sy >> 5)
+    np.testing.assert_array_equal(((hi >> 5) & 31).reshape(6, w, w), ref_sx & 31)
+    np.testing.assert_array_equal((hi & 31).reshape(6, w, w), ref_sy & 31)
+    sx, sy = oe2c.fixed_maps(w, H, W)
+    np.testing.assert_array_equal(sx.reshape(6, w, w), ref_sx)
+    np.testing.assert_array_equal(sy.reshape(6, w, w), ref_sy)
+
+
 @pytest.mark.parametrize("w,C", [(2, 3), (3, 4), (5, 2), (6, 7), (9, 3), (11, 2), (12, 5), (20, 2)])
 def test_c2e_maps_and_output_live(ref, w, C):
     """utils/cube_to_equi.py:12-66: face map exact, out_coord to 1e-12, the host sampling plan's normaliser M, and
