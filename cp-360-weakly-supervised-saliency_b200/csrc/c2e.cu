@@ -14,9 +14,14 @@
 //   c2e_bwd_kernel   bilinear scatter-add of the output gradient (training path)
 //   c2e_cubic_*      Cube2Equi.to_equi_cv2 (cube_to_equi.py:68-91): cv2.remap(INTER_CUBIC) arithmetic
 #include <algorithm>
+#include <stdlib.h>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "tma.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cp360 {
 
@@ -32,8 +37,11 @@ __device__ __forceinline__ Tap decode_tap(uint32_t t) {
   return r;
 }
 
-// float max through integer atomics (order-preserving for non-NaN values)
+// float max through integer atomics, with torch.max's NaN semantics: a NaN beats every number. As an int the
+// canonical quiet NaN 0x7fc00000 is above +inf, so atomicMax keeps it against every non-negative value, and as
+// an unsigned word it is below every negative float's pattern, so the atomicMin of the negative branch keeps it too.
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v != v) { atomicMax(reinterpret_cast<int*>(addr), 0x7fc00000); return; }
   v += 0.0f;   // -0.0 -> +0.0
   if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
@@ -41,12 +49,29 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 
 // (value, channel) keys for the arg-max variant: order-preserving map of the float into the high word,
 // ~channel in the low word, so a 64-bit atomicMax keeps the largest value and, among equal values,
-// the LOWEST channel (torch.max(dim) returns the first maximal index). Every key is > 0.
+// the LOWEST channel (torch.max(dim) returns the first maximal index). NaN is canonicalised to the quiet NaN
+// above +inf, so the first NaN channel wins, as in torch. Every key is > 0.
 __device__ __forceinline__ unsigned long long argmax_key(float v, int c) {
+  if (v != v) v = __int_as_float(0x7fc00000);
   v += 0.0f;
   const uint32_t b = __float_as_uint(v);
   const uint32_t o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
   return ((unsigned long long)o << 32) | (uint32_t)(0xffffffffu - (uint32_t)c);
+}
+
+// running (max, arg-max) update with torch.max(dim) semantics: strictly greater replaces (first maximal index
+// wins), a NaN replaces any number and is never replaced (first NaN wins)
+__device__ __forceinline__ void max_update(float acc, int c, float& best, int& best_c) {
+  if ((acc > best || acc != acc) && best == best) { best = acc; best_c = c; }
+}
+__device__ __forceinline__ float max_nan(float a, float b) {      // NaN-propagating max
+  return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
+}
+// is (av, ac) a better (max, index) pair than (bv, bc)?
+__device__ __forceinline__ bool pair_better(float av, int ac, float bv, int bc) {
+  const bool an = av != av, bn = bv != bv;
+  if (an || bn) return an && (!bn || ac < bc);
+  return av > bv || (av == bv && ac < bc);
 }
 
 __global__ void c2e_argmax_decode_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ sal,
@@ -103,8 +128,8 @@ c2e_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
       if (sw_ok) acc = fmaf(__ldg(src + w), wt.z, acc);
       if (se_ok) acc = fmaf(__ldg(src + w + 1), wt.w, acc);
       if (MODE == 0) __stcs(out + (b * C + c) * (int64_t)P + pix, acc);
-      else if (MODE == 1) best = fmaxf(best, acc);
-      else if (acc > best) { best = acc; best_c = c; }
+      else if (MODE == 1) best = max_nan(best, acc);
+      else max_update(acc, c, best, best_c);
     }
     if (MODE == 1) atomic_max_float(out + b * (int64_t)P + pix, best);
     if (MODE == 2) atomicMax(reinterpret_cast<unsigned long long*>(out) + b * (int64_t)P + pix, argmax_key(best, best_c));
@@ -175,8 +200,8 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
       if (sw_ok) acc = fmaf(src[o_sw], wt.z, acc);
       if (se_ok) acc = fmaf(src[o_se], wt.w, acc);
       if (MODE == 0) __stcs(dst + (int64_t)c * P, acc);
-      else if (MODE == 1) best = fmaxf(best, acc);
-      else if (acc > best) { best = acc; best_c = c; }
+      else if (MODE == 1) best = max_nan(best, acc);
+      else max_update(acc, c, best, best_c);
     }
     if (MODE == 1) atomic_max_float(out + (int64_t)b * P + pix, best);
     if (MODE == 2) atomicMax(reinterpret_cast<unsigned long long*>(out) + (int64_t)b * P + pix, argmax_key(best, c0 + best_c));
@@ -184,55 +209,384 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
   CP360_TRACE_T0(3);
 }
 
-__global__ void __launch_bounds__(kC2eThreads)
-c2e_bwd_kernel(const float* __restrict__ gequi, const uint32_t* __restrict__ taps,
-               const float4* __restrict__ wts, float* __restrict__ gcube, int64_t B, int C, int w,
-               int ch_per_block) {
-  const int P = 8 * w * w, ww = w * w;
-  const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
-  if (pix >= P) return;
-  const Tap t = decode_tap(__ldg(taps + pix));
-  const float4 wt = __ldg(wts + pix);
-  const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
-  const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
-  const int o_nw = t.y0 * w + t.x0;
-  const int c_begin = blockIdx.y * ch_per_block, c_end = min(C, c_begin + ch_per_block);
-  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
-    float* dst = gcube + ((b * 6 + t.face) * C + c_begin) * (int64_t)ww + o_nw;
-    for (int c = c_begin; c < c_end; ++c, dst += ww) {
-      const float g = __ldg(gequi + (b * C + c) * (int64_t)P + pix);
-      if (xw_ok && yn_ok) atomicAdd(dst, g * wt.x);
-      if (xe_ok && yn_ok) atomicAdd(dst + 1, g * wt.y);
-      if (xw_ok && ys_ok) atomicAdd(dst + w, g * wt.z);
-      if (xe_ok && ys_ok) atomicAdd(dst + w + 1, g * wt.w);
+// ---- K3m, small faces (w <= 16): channel max WITHOUT atomics, fill pass or scratch ----------------------------
+// A cluster of G CTAs owns one frame; CTA r streams channels [r*Cg, (r+1)*Cg) of all six faces through a ring of
+// TMA bulk-loaded stages (K channels each) while its threads — one per output pixel (up to kC2eMaxPix per thread
+// at w = 16) — keep the running max (and arg-max channel) in registers. The G partial maps meet in distributed
+// shared memory: after a cluster barrier CTA r combines its slice of the pixels, G lanes per pixel each reading one
+// CTA's partial through DSMEM and a warp-shuffle max (north_star (c)) over those lanes; one lane stores the result.
+// Deterministic, NaN-propagating like torch.max (test_temporal.py:83), and the output is written exactly once.
+constexpr int kC2eMaxPix = 4;          // pixels per thread: 8 w^2 / 512 at w = 16
+constexpr int kC2eMaxStages = 4;
+
+struct C2eMaxArgs {
+  const float* cube;
+  const uint32_t* taps;
+  const float4* wts;
+  float* sal;
+  int32_t* arg;          // MODE 2 only
+  int C, w;
+  int Cg;                // channels per CTA (multiple of the bulk-copy quantum)
+  int K;                 // channels per stage
+  int stages;
+  int ring_off;          // byte offset of the ring in dynamic shared memory
+  int stage_floats;      // 6 * K * w * w + skew
+};
+
+template <int MODE, int NPIX>
+__global__ void __launch_bounds__(kC2eSmallThreads)
+c2e_max_cluster_kernel(const C2eMaxArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int G = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  const int w = a.w, ww = w * w, P = 8 * ww;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                    // [stages]
+  float* part_val = reinterpret_cast<float*>(smem_raw + 64);                 // [P]
+  int* part_arg = reinterpret_cast<int*>(part_val + P);                      // [P] (MODE 2)
+  float* ring = reinterpret_cast<float*>(smem_raw + a.ring_off);
+  const int b = blockIdx.x / G;
+  const int c_begin = min(r * a.Cg, a.C), c_end = min(c_begin + a.Cg, a.C);
+  const int n_st = (c_end - c_begin + a.K - 1) / a.K;
+  const int tid = threadIdx.x;
+  const int fstride = a.K * ww;                                             // face stride inside a stage
+
+  pdl_trigger();
+  auto issue = [&](int i) {                                                  // thread 0: stage i of this CTA
+    const int s = i % a.stages;
+    const int c0 = c_begin + i * a.K, kl = min(a.K, c_end - c0);
+    const uint32_t bytes = (uint32_t)(kl * ww) * 4u;
+    tma::mbar_expect_tx(&full[s], 6u * bytes);
+    float* dst = ring + (size_t)s * a.stage_floats;
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      tma::bulk_load(dst + (size_t)f * fstride + kFaceSkew[f], a.cube + (((int64_t)b * 6 + f) * a.C + c0) * ww, bytes, &full[s]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0)
+    for (int i = 0; i < min(a.stages, n_st); ++i) issue(i);
+
+  // this thread's pixels: plan entries live in registers for the whole kernel
+  int off[NPIX][4];
+  float wt[NPIX][4];
+  int foff[NPIX];
+  float best[NPIX];
+  int best_c[NPIX];
+#pragma unroll
+  for (int k = 0; k < NPIX; ++k) {
+    const int pix = tid + k * kC2eSmallThreads;
+    best[k] = -INFINITY;
+    best_c[k] = c_begin;
+    foff[k] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { off[k][j] = 0; wt[k][j] = 0.0f; }
+    if (pix < P) {
+      const Tap t = decode_tap(__ldg(a.taps + pix));
+      const float4 w4 = __ldg(a.wts + pix);
+      const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
+      const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
+      // out-of-face taps: address clamped into the face, weight zeroed — 0 * finite = 0 is what skipping the tap
+      // gives, and an Inf / NaN sitting at the clamped address must not leak in, so those taps are predicated below
+      const int xw = xw_ok ? t.x0 : 0, xe = xe_ok ? t.x0 + 1 : 0, yn = yn_ok ? t.y0 : 0, ys = ys_ok ? t.y0 + 1 : 0;
+      off[k][0] = yn * w + xw; off[k][1] = yn * w + xe; off[k][2] = ys * w + xw; off[k][3] = ys * w + xe;
+      wt[k][0] = w4.x; wt[k][1] = w4.y; wt[k][2] = w4.z; wt[k][3] = w4.w;
+      const unsigned ok = (unsigned)(xw_ok && yn_ok) | (unsigned)(xe_ok && yn_ok) << 1 | (unsigned)(xw_ok && ys_ok) << 2 |
+                          (unsigned)(xe_ok && ys_ok) << 3;
+      foff[k] = (t.face * fstride + kFaceSkew[t.face]) | (int)(ok << 24);
     }
+  }
+
+  for (int i = 0; i < n_st; ++i) {
+    const int s = i % a.stages;
+    tma::mbar_wait(&full[s], (uint32_t)((i / a.stages) & 1));
+    const int c0 = c_begin + i * a.K, kl = min(a.K, c_end - c0);
+    const float* st = ring + (size_t)s * a.stage_floats;
+#pragma unroll
+    for (int k = 0; k < NPIX; ++k) {
+      if (NPIX > 1 && tid + k * kC2eSmallThreads >= P) break;
+      const unsigned ok = (unsigned)foff[k] >> 24;
+      const float* src = st + (foff[k] & 0xffffff);
+      float bv = best[k];
+      int bc = best_c[k];
+#pragma unroll 4
+      for (int c = 0; c < kl; ++c, src += ww) {
+        float acc = 0.0f;                      // order of torch's grid_sampler CUDA kernel
+        if (ok & 1u) acc = fmaf(src[off[k][0]], wt[k][0], acc);
+        if (ok & 2u) acc = fmaf(src[off[k][1]], wt[k][1], acc);
+        if (ok & 4u) acc = fmaf(src[off[k][2]], wt[k][2], acc);
+        if (ok & 8u) acc = fmaf(src[off[k][3]], wt[k][3], acc);
+        if (MODE == 1) bv = max_nan(bv, acc);
+        else max_update(acc, c0 + c, bv, bc);
+      }
+      best[k] = bv;
+      best_c[k] = bc;
+    }
+    __syncthreads();                                     // every thread is done with stage s
+    if (tid == 0 && i + a.stages < n_st) issue(i + a.stages);
+  }
+#pragma unroll
+  for (int k = 0; k < NPIX; ++k) {
+    const int pix = tid + k * kC2eSmallThreads;
+    if (pix < P) {
+      part_val[pix] = best[k];
+      if (MODE == 2) part_arg[pix] = best_c[k];
+    }
+  }
+  cluster.sync();                                        // all G partial maps are in place (release / acquire)
+
+  // combine: CTA r owns pixels [r*Pr, (r+1)*Pr); G consecutive lanes serve one pixel, lane j reads CTA j's partial
+  const int Pr = (P + G - 1) / G;
+  for (int q0 = 0; q0 < Pr * G; q0 += kC2eSmallThreads) {       // warp-uniform trip count: every lane shuffles
+    const int q = q0 + tid;
+    const int j = q % G, pix = r * Pr + q / G;
+    const bool live = q < Pr * G && pix < P;
+    float v = -INFINITY;
+    int vc = 0x7fffffff;
+    if (live) {
+      v = *cluster.map_shared_rank(part_val + pix, j);
+      if (MODE == 2) vc = *cluster.map_shared_rank(part_arg + pix, j);
+    }
+    for (int d = G >> 1; d > 0; d >>= 1) {               // G is a power of two <= 8: the group never straddles a warp
+      const float ov = __shfl_xor_sync(0xffffffffu, v, d);
+      if (MODE == 2) {
+        const int oc = __shfl_xor_sync(0xffffffffu, vc, d);
+        if (pair_better(ov, oc, v, vc)) { v = ov; vc = oc; }
+      } else {
+        v = max_nan(v, ov);
+      }
+    }
+    if (j == 0 && live) {
+      a.sal[(int64_t)b * P + pix] = v;
+      if (MODE == 2) a.arg[(int64_t)b * P + pix] = vc;
+    }
+  }
+  cluster.sync();                                        // nobody exits while a neighbour may still read its partials
+}
+
+// ---- K3m for the reference's own map sizes (w <= 8): lane = channel, warp = output pixel ------------------------
+// With a thread per pixel (kernel above) the 32 lanes of every shared-memory load read the SAME 49- / 64-word channel
+// plane and collide in its banks; the kernel then sits on shared-memory bandwidth (measured: 1.7 TB/s of DRAM-side
+// bytes at [192,1000,8,8], ~2 wavefronts per load). Here the 32 lanes of a warp hold 32 CHANNELS of one pixel: the
+// channel planes are laid out with an ODD stride, so the four tap loads of a pixel are conflict-free, the pixel's
+// plan entry is a warp-uniform broadcast, and the channel max is a WARP-SHUFFLE reduction over the lanes
+// (north_star (c)), done once per pixel after the last stage — between stages every lane keeps its own running
+// max (and arg-max channel) for each of the warp's pixels in registers. Planes arrive through cp.async (4 B
+// granules: the padded layout cannot be a bulk copy) in a two-stage ring. Channel split across a cluster, DSMEM
+// combine and NaN semantics as in c2e_max_cluster_kernel. Any C, any alignment.
+constexpr int kLanechPixPerWarp = 32;         // 8 w^2 / 16 warps at w = 8
+constexpr int kLanechK = 32;                  // channels per stage = lanes
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tma::smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kC2eSmallThreads, 1)
+c2e_max_lanech_kernel(const C2eMaxArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int G = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  const int w = a.w, ww = w * w, P = 8 * ww, S = ww | 1;
+  float4* wt_s = reinterpret_cast<float4*>(smem_raw);                        // [P] bilinear weights nw, ne, sw, se
+  uint32_t* tap_s = reinterpret_cast<uint32_t*>(wt_s + P);                   // [P] face:3 | ok:4 | off3..off0 (6 bits each)
+  float* part_val = reinterpret_cast<float*>(tap_s + P);                     // [P]
+  int* part_arg = reinterpret_cast<int*>(part_val + P);                      // [P] (MODE 2)
+  float* ring = reinterpret_cast<float*>(smem_raw + a.ring_off);             // [2][6][32][S]
+  const int b = blockIdx.x / G;
+  const int c_begin = min(r * a.Cg, a.C), c_end = min(c_begin + a.Cg, a.C);
+  const int n_st = (c_end - c_begin + kLanechK - 1) / kLanechK;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inv_ww = 1.0f / (float)ww;
+
+  pdl_trigger();
+  for (int pix = tid; pix < P; pix += kC2eSmallThreads) {                     // plan table (independent of the data)
+    const Tap t = decode_tap(__ldg(a.taps + pix));
+    const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
+    const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
+    const int xw = xw_ok ? t.x0 : 0, xe = xe_ok ? t.x0 + 1 : 0, yn = yn_ok ? t.y0 : 0, ys = ys_ok ? t.y0 + 1 : 0;
+    const uint32_t ok = (uint32_t)(xw_ok && yn_ok) | (uint32_t)(xe_ok && yn_ok) << 1 | (uint32_t)(xw_ok && ys_ok) << 2 |
+                        (uint32_t)(xe_ok && ys_ok) << 3;
+    tap_s[pix] = (uint32_t)t.face << 28 | ok << 24 | (uint32_t)(ys * w + xe) << 18 | (uint32_t)(ys * w + xw) << 12 |
+                 (uint32_t)(yn * w + xe) << 6 | (uint32_t)(yn * w + xw);
+    wt_s[pix] = __ldg(a.wts + pix);
+  }
+  pdl_wait();
+
+  auto issue = [&](int i) {                                                   // all threads: stage i -> ring[i & 1]
+    const int c0 = c_begin + i * kLanechK, kl = min(kLanechK, c_end - c0);
+    float* dst = ring + (size_t)(i & 1) * 6 * kLanechK * S;
+    const int n = kl * ww;
+    for (int f = 0; f < 6; ++f) {
+      const float* src = a.cube + (((int64_t)b * 6 + f) * a.C + c0) * ww;
+      float* df = dst + f * kLanechK * S;
+      for (int e = tid; e < n; e += kC2eSmallThreads) {
+        const int c = (int)(((float)e + 0.5f) * inv_ww);                      // e / ww, exact for these sizes
+        cp_async4(df + e + c * (S - ww), src + e);
+      }
+    }
+    cp_async_commit();
+  };
+
+  float best[kLanechPixPerWarp];
+  int best_c[MODE == 2 ? kLanechPixPerWarp : 1];
+#pragma unroll
+  for (int j = 0; j < kLanechPixPerWarp; ++j) {
+    best[j] = -INFINITY;
+    if (MODE == 2) best_c[j] = 0x7fffffff;
+  }
+  if (n_st > 0) issue(0);
+  for (int i = 0; i < n_st; ++i) {
+    if (i + 1 < n_st) { issue(i + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                                          // stage i is in place for every thread
+    const int c0 = c_begin + i * kLanechK, kl = min(kLanechK, c_end - c0);
+    const float* st = ring + (size_t)(i & 1) * 6 * kLanechK * S + lane * S;
+    const bool live = lane < kl;
+#pragma unroll
+    for (int j = 0; j < kLanechPixPerWarp; ++j) {
+      const int q = warp + j * (kC2eSmallThreads / 32);
+      if (q < P) {                                                            // warp-uniform
+        const uint32_t t = tap_s[q];
+        const float4 wt = wt_s[q];
+        const float* src = st + (t >> 28) * (kLanechK * S);
+        float acc = 0.0f;                      // order of torch's grid_sampler CUDA kernel
+        if (t & (1u << 24)) acc = fmaf(src[t & 63u], wt.x, acc);
+        if (t & (2u << 24)) acc = fmaf(src[(t >> 6) & 63u], wt.y, acc);
+        if (t & (4u << 24)) acc = fmaf(src[(t >> 12) & 63u], wt.z, acc);
+        if (t & (8u << 24)) acc = fmaf(src[(t >> 18) & 63u], wt.w, acc);
+        if (live) {
+          if (MODE == 1) best[j] = max_nan(best[j], acc);
+          else max_update(acc, c0 + lane, best[j], best_c[j]);
+        }
+      }
+    }
+    __syncthreads();                                                          // ring[i & 1] may be refilled (stage i + 2)
+  }
+  // channel max over the 32 lanes: warp shuffles; lane 0 publishes the CTA's partial
+#pragma unroll
+  for (int j = 0; j < kLanechPixPerWarp; ++j) {
+    const int q = warp + j * (kC2eSmallThreads / 32);
+    if (q < P) {
+      float v = best[j];
+      int vc = MODE == 2 ? best_c[j] : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, d);
+        if (MODE == 2) {
+          const int oc = __shfl_xor_sync(0xffffffffu, vc, d);
+          if (pair_better(ov, oc, v, vc)) { v = ov; vc = oc; }
+        } else {
+          v = max_nan(v, ov);
+        }
+      }
+      if (lane == 0) {
+        part_val[q] = v;
+        if (MODE == 2) part_arg[q] = vc;
+      }
+    }
+  }
+  cluster.sync();                                        // all G partial maps are in place (release / acquire)
+  const int Pr = (P + G - 1) / G;
+  for (int q0 = 0; q0 < Pr * G; q0 += kC2eSmallThreads) {       // warp-uniform trip count: every lane shuffles
+    const int q = q0 + tid;
+    const int j = q % G, pix = r * Pr + q / G;
+    const bool live = q < Pr * G && pix < P;
+    float v = -INFINITY;
+    int vc = 0x7fffffff;
+    if (live) {
+      v = *cluster.map_shared_rank(part_val + pix, j);
+      if (MODE == 2) vc = *cluster.map_shared_rank(part_arg + pix, j);
+    }
+    for (int d = G >> 1; d > 0; d >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, d);
+      if (MODE == 2) {
+        const int oc = __shfl_xor_sync(0xffffffffu, vc, d);
+        if (pair_better(ov, oc, v, vc)) { v = ov; vc = oc; }
+      } else {
+        v = max_nan(v, ov);
+      }
+    }
+    if (j == 0 && live) {
+      a.sal[(int64_t)b * P + pix] = v;
+      if (MODE == 2) a.arg[(int64_t)b * P + pix] = vc;
+    }
+  }
+  cluster.sync();                                        // nobody exits while a neighbour may still read its partials
+}
+
+// ---- backward of c2e as a GATHER over the transposed plan (cp360_c2e_build_bwd_plan): no atomics, fixed
+// summation order -> bit-reproducible gradients. Block = (frame, channel group); a thread owns cube pixels and
+// walks its contributors once, accumulating KCH channels in registers. SMALL: the gradient planes of the group
+// are staged in shared memory by one bulk copy (w <= 16), else they are read through the read-only path.
+template <int KCH, bool SMALL>
+__global__ void __launch_bounds__(kC2eSmallThreads)
+c2e_bwd_gather_kernel(const float* __restrict__ gequi, const int32_t* __restrict__ offs, const int32_t* __restrict__ pix,
+                      const float* __restrict__ wts, float* __restrict__ gcube, int C, int w, int groups) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  const float* gs = reinterpret_cast<const float*>(smem_raw + 128);       // [KCH][P] (SMALL)
+  const int ww = w * w, P = 8 * ww, NC = 6 * ww;
+  const int b = blockIdx.x / groups, c0 = (blockIdx.x - b * groups) * KCH;
+  const int kl = min(KCH, C - c0);
+  const float* src = gequi + ((int64_t)b * C + c0) * P;
+  if (SMALL) {
+    if (threadIdx.x == 0) {
+      tma::mbar_init(bar, 1);
+      tma::fence_mbar_init();
+      const uint32_t bytes = (uint32_t)(kl * P) * 4u;
+      tma::mbar_expect_tx(bar, bytes);
+      tma::bulk_load(const_cast<float*>(gs), src, bytes, bar);
+    }
+    __syncthreads();
+    tma::mbar_wait(bar, 0);
+    src = gs;
+  }
+  for (int cell = threadIdx.x; cell < NC; cell += kC2eSmallThreads) {
+    float acc[KCH];
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) acc[c] = 0.0f;
+    const int e0 = __ldg(offs + cell), e1 = __ldg(offs + cell + 1);
+    for (int e = e0; e < e1; ++e) {
+      const int p = __ldg(pix + e);
+      const float wt = __ldg(wts + e);
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        if (c < kl) acc[c] = fmaf(SMALL ? src[c * P + p] : __ldg(src + (int64_t)c * P + p), wt, acc[c]);
+    }
+    const int f = cell / ww, r = cell - f * ww;
+    float* dst = gcube + (((int64_t)b * 6 + f) * C + c0) * ww + r;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c)
+      if (c < kl) __stcs(dst + (int64_t)c * ww, acc[c]);
   }
 }
 
-// Backward of the fused back-projection + channel max: the gradient of sal[b,pix] flows to the four
-// taps of channel arg[b,pix] only (torch.max backward + grid_sample backward,
-// train_temporal.py:105-107). gcube is zero-filled by the caller-side memset of the launch.
+// backward of the fused channel max, single-owner form: a thread owns one cube pixel of one frame and adds the
+// routed gradients of its contributors (gsal[b,p] * weight into channel argmax[b,p]) one after the other — no two
+// threads ever write the same element, so no atomics and a fixed summation order. gcube is zero-filled first.
 __global__ void __launch_bounds__(kC2eThreads)
-c2e_max_bwd_kernel(const float* __restrict__ gsal, const int32_t* __restrict__ arg,
-                   const uint32_t* __restrict__ taps, const float4* __restrict__ wts,
-                   float* __restrict__ gcube, int64_t B, int C, int w) {
-  const int P = 8 * w * w, ww = w * w;
-  const int pix = blockIdx.x * kC2eThreads + threadIdx.x;
-  if (pix >= P) return;
-  const Tap t = decode_tap(__ldg(taps + pix));
-  const float4 wt = __ldg(wts + pix);
-  const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
-  const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
-  const int o_nw = t.y0 * w + t.x0;
+c2e_max_bwd_gather_kernel(const float* __restrict__ gsal, const int32_t* __restrict__ arg, const int32_t* __restrict__ offs,
+                          const int32_t* __restrict__ pix, const float* __restrict__ wts, float* __restrict__ gcube,
+                          int64_t B, int C, int w) {
+  const int ww = w * w, P = 8 * ww, NC = 6 * ww;
+  const int cell = blockIdx.x * kC2eThreads + threadIdx.x;
+  if (cell >= NC) return;
+  const int e0 = __ldg(offs + cell), e1 = __ldg(offs + cell + 1);
+  const int f = cell / ww, r = cell - f * ww;
   for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
-    const int c = __ldg(arg + b * (int64_t)P + pix);
-    if ((unsigned)c >= (unsigned)C) continue;          // never produced by the forward; guards foreign input
-    const float g = __ldg(gsal + b * (int64_t)P + pix);
-    float* dst = gcube + ((b * 6 + t.face) * C + c) * (int64_t)ww + o_nw;
-    if (xw_ok && yn_ok) atomicAdd(dst, g * wt.x);
-    if (xe_ok && yn_ok) atomicAdd(dst + 1, g * wt.y);
-    if (xw_ok && ys_ok) atomicAdd(dst + w, g * wt.z);
-    if (xe_ok && ys_ok) atomicAdd(dst + w + 1, g * wt.w);
+    float* base = gcube + ((b * 6 + f) * C) * (int64_t)ww + r;
+    for (int e = e0; e < e1; ++e) {
+      const int p = __ldg(pix + e);
+      const int c = __ldg(arg + b * (int64_t)P + p);
+      if ((unsigned)c >= (unsigned)C) continue;          // never produced by the forward; guards foreign input
+      base[(int64_t)c * ww] += __ldg(gsal + b * (int64_t)P + p) * __ldg(wts + e);
+    }
   }
 }
 
@@ -348,6 +702,96 @@ c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restric
   }
 }
 
+// w <= 8 (the reference's 7x7 / 8x8 score maps): lane = channel, warp = output pixel. With lanes on pixels
+// (kernel above) the 32 lanes of a load all hit the same 49- / 64-word channel plane and collide in its banks
+// (~3 wavefronts per load, measured: the kernel sat on shared-memory bandwidth at 0.7 TB/s); with lanes on
+// channels and an ODD plane stride every load is conflict-free, the 16 window weights of a pixel are warp-uniform
+// (a per-CTA table, read as broadcasts), and the interior / border summation orders of OpenCV become a
+// warp-uniform branch. Block = (frame, 32 channels): planes come in through coalesced loads into the padded
+// layout, results leave through a [32][tile] staging tile so that global stores stay coalesced.
+constexpr int kCubicLaneThreads = 512;
+constexpr int kCubicTilePix = 256;
+
+__global__ void __launch_bounds__(kCubicLaneThreads)
+c2e_cubic_lanech_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
+                        float* __restrict__ out, int C, int w, int groups) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int ww = w * w, P = 8 * ww;
+  const int S = ww | 1;                                       // odd channel-plane stride: conflict-free across lanes
+  float* in_s = reinterpret_cast<float*>(smem_raw);           // [6][32][S]
+  float4* wt_s = reinterpret_cast<float4*>(in_s + ((6 * 32 * S + 3) & ~3));    // [P][4] : 16 weights per pixel
+  float* out_s = reinterpret_cast<float*>(wt_s + (size_t)P * 4);               // [32][kCubicTilePix + 1]
+  const int b = blockIdx.x / groups, c0 = (blockIdx.x - b * groups) * 32;
+  const int kl = min(32, C - c0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  // weight table (independent of the data): thread = pixel
+  for (int pix = tid; pix < P; pix += kCubicLaneThreads) {
+    const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
+    float cx[4], cy[4];
+    cubic_coeffs(t.fx, cx);
+    cubic_coeffs(t.fy, cy);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      wt_s[pix * 4 + i] = make_float4(__fmul_rn(cy[i], cx[0]), __fmul_rn(cy[i], cx[1]), __fmul_rn(cy[i], cx[2]),
+                                      __fmul_rn(cy[i], cx[3]));
+  }
+  pdl_wait();
+  // planes: coalesced global loads, one channel plane after the other, into the padded layout
+  for (int f = 0; f < 6; ++f) {
+    const float* src = cube + (((int64_t)b * 6 + f) * C + c0) * ww;
+    for (int e = tid; e < kl * ww; e += kCubicLaneThreads) {
+      const int c = e / ww, r = e - c * ww;
+      in_s[(f * 32 + c) * S + r] = __ldg(src + e);
+    }
+  }
+  __syncthreads();
+  const int lim = max(w - 3, 0);
+  const float* lane_in = in_s + lane * S;
+  for (int p0 = 0; p0 < P; p0 += kCubicTilePix) {
+    const int np = min(kCubicTilePix, P - p0);
+    for (int q = warp; q < np; q += kCubicLaneThreads / 32) {
+      const int pix = p0 + q;
+      const CubicTap t = decode_cubic_tap(__ldg(taps + pix));           // warp-uniform
+      const float* src = lane_in + t.face * 32 * S;
+      float wt[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = wt_s[pix * 4 + i];
+        wt[i * 4] = v.x; wt[i * 4 + 1] = v.y; wt[i * 4 + 2] = v.z; wt[i * 4 + 3] = v.w;
+      }
+      float sum = 0.0f;
+      if ((unsigned)t.x0 < (unsigned)lim && (unsigned)t.y0 < (unsigned)lim) {   // window inside the face: row sums
+        const float* r0 = src + t.y0 * w + t.x0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* r = r0 + i * w;
+          float rs = __fadd_rn(__fmul_rn(r[0], wt[i * 4]), __fmul_rn(r[1], wt[i * 4 + 1]));
+          rs = __fadd_rn(rs, __fmul_rn(r[2], wt[i * 4 + 2]));
+          rs = __fadd_rn(rs, __fmul_rn(r[3], wt[i * 4 + 3]));
+          sum = i == 0 ? rs : __fadd_rn(sum, rs);
+        }
+      } else {                                                                 // border: tap by tap, outside taps skipped
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int yy = t.y0 + i, xx = t.x0 + j;
+            if ((unsigned)yy < (unsigned)w && (unsigned)xx < (unsigned)w)
+              sum = __fadd_rn(sum, __fmul_rn(src[yy * w + xx], wt[i * 4 + j]));
+          }
+      }
+      out_s[lane * (kCubicTilePix + 1) + q] = sum;
+    }
+    __syncthreads();
+    for (int e = tid; e < kl * np; e += kCubicLaneThreads) {
+      const int c = e / np, q = e - c * np;
+      __stcs(out + ((int64_t)b * C + c0 + c) * P + p0 + q, out_s[c * (kCubicTilePix + 1) + q]);
+    }
+    __syncthreads();
+  }
+}
+
 // any w: taps read through the read-only path (the cube of one frame is L2-resident)
 __global__ void __launch_bounds__(kC2eThreads)
 c2e_cubic_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
@@ -425,6 +869,83 @@ static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts,
   return CP360_OK;
 }
 
+// K3m through the cluster kernel; returns false (nothing launched) when it does not apply.
+template <int MODE>
+static bool try_c2e_max_cluster(const float* cube, const uint32_t* taps, const float* wts, float* sal, int32_t* arg,
+                                int64_t B, int64_t C, int w, cudaStream_t st, int* rc_out) {
+  static const bool enabled = [] { const char* v = getenv("CP360_C2E_CLUSTER"); return !(v && *v == '0'); }();
+  if (!enabled || w > 16 || B > 0x3fffffff) return false;
+  const int ww = w * w, P = 8 * ww;
+  static const bool lanech = [] { const char* v = getenv("CP360_C2E_LANECH"); return !(v && *v == '0'); }();
+  if (w <= 8 && lanech) {                              // lane = channel kernel: any C, any alignment
+    C2eMaxArgs a;
+    a.cube = cube; a.taps = taps; a.wts = reinterpret_cast<const float4*>(wts); a.sal = sal; a.arg = arg;
+    a.C = (int)C; a.w = w; a.K = kLanechK; a.stages = 2;
+    int G = 8;
+    while (G > 1 && (B * G > 4 * (int64_t)sm_count() || (C + G - 1) / G < kLanechK)) G >>= 1;
+    a.Cg = (int)((C + G - 1) / G);
+    const int S = ww | 1;
+    a.stage_floats = 6 * kLanechK * S;
+    a.ring_off = (P * (16 + 4 + 4 + 4) + 127) & ~127;
+    const size_t smem = (size_t)a.ring_off + (size_t)2 * a.stage_floats * 4;
+    void (*kern)(const C2eMaxArgs) = c2e_max_lanech_kernel<MODE>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    cudaError_t e = launch_kernel_cluster(kern, dim3((unsigned)(B * G)), dim3(kC2eSmallThreads), smem, st, (unsigned)G, a);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("c2e cluster launch failed: %s", cudaGetErrorString(e));
+      *rc_out = CP360_ERR_CUDA;
+      return true;
+    }
+    count_launch();
+    *rc_out = CP360_OK;
+    return true;
+  }
+  if (((uintptr_t)cube % 16) != 0) return false;
+  int q = 1;
+  while ((q * ww) % 4) q <<= 1;                       // 16 B granularity of the bulk copies
+  if (C % q) return false;
+  C2eMaxArgs a;
+  a.cube = cube; a.taps = taps; a.wts = reinterpret_cast<const float4*>(wts); a.sal = sal; a.arg = arg;
+  a.C = (int)C; a.w = w;
+  a.K = std::max(q, (int)((24 * 1024) / (6 * ww * 4)) / q * q);
+  int G = 8;
+  while (G > 1 && (B * G > 4 * (int64_t)sm_count() || (C + G - 1) / G < a.K)) G >>= 1;   // enough CTAs, >= one stage each
+  a.Cg = (int)(((C + G - 1) / G + q - 1) / q * q);
+  a.K = std::min(a.K, a.Cg);
+  a.stages = 3;
+  a.stage_floats = 6 * a.K * ww + kFaceSkewMax;
+  a.ring_off = (64 + 8 * P + 127) & ~127;
+  const size_t smem = (size_t)a.ring_off + (size_t)a.stages * a.stage_floats * 4;
+  if (smem > 200 * 1024) return false;
+  void (*kern)(const C2eMaxArgs) = P <= kC2eSmallThreads ? c2e_max_cluster_kernel<MODE, 1> : c2e_max_cluster_kernel<MODE, kC2eMaxPix>;
+  if (P > kC2eSmallThreads * kC2eMaxPix) return false;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaError_t e = launch_kernel_cluster(kern, dim3((unsigned)(B * G)), dim3(kC2eSmallThreads), smem, st, (unsigned)G, a);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("c2e cluster launch failed: %s", cudaGetErrorString(e));
+    *rc_out = CP360_ERR_CUDA;
+    return true;
+  }
+  count_launch();
+  *rc_out = CP360_OK;
+  return true;
+}
+
+static int check_bwd_plan(const void* offs, const void* pix, const void* wts) {
+  CP360_CHECK_ARG(offs && pix && wts, CP360_ERR_BAD_ARG, "null backward plan");
+  CP360_CHECK_ARG(((uintptr_t)offs % 4) == 0 && ((uintptr_t)pix % 4) == 0 && ((uintptr_t)wts % 4) == 0, CP360_ERR_ALIGN,
+                  "backward plan must be 4 B aligned");
+  return CP360_OK;
+}
+
 }  // namespace cp360
 
 using namespace cp360;
@@ -444,6 +965,8 @@ int cp360_c2e_max_fwd(const float* cube, const uint32_t* taps, const float* wts,
   if (rc != CP360_OK || B == 0) return rc;
   CP360_CHECK_ARG(C > 0, CP360_ERR_BAD_ARG, "channel max over zero channels");
   cudaStream_t st = (cudaStream_t)stream;
+  if (try_c2e_max_cluster<1>(cube, taps, wts, sal, nullptr, B, C, w, st, &rc)) return rc;
+  // large faces: -inf fill, then per-chunk running maxima combined with an order-preserving atomic max
   const int64_t n = B * 8 * (int64_t)w * w;
   launch_kernel(fill_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st, sal, n, -INFINITY);
   CP360_LAUNCHED();
@@ -455,10 +978,11 @@ int cp360_c2e_max_arg_fwd(const float* cube, const uint32_t* taps, const float* 
   int rc = check_common(cube, taps, wts, sal, B, C, w);
   if (rc != CP360_OK || B == 0) return rc;
   CP360_CHECK_ARG(C > 0, CP360_ERR_BAD_ARG, "channel max over zero channels");
-  CP360_CHECK_ARG(argmax && scratch, CP360_ERR_BAD_ARG, "null pointer");
-  CP360_CHECK_ARG(((uintptr_t)scratch % 8) == 0 && ((uintptr_t)argmax % 4) == 0, CP360_ERR_ALIGN,
-                  "scratch must be 8 B aligned, argmax 4 B aligned");
+  CP360_CHECK_ARG(argmax && ((uintptr_t)argmax % 4) == 0, CP360_ERR_BAD_ARG, "argmax null or misaligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (try_c2e_max_cluster<2>(cube, taps, wts, sal, argmax, B, C, w, st, &rc)) return rc;   // w <= 16: no scratch needed
+  CP360_CHECK_ARG(scratch && ((uintptr_t)scratch % 8) == 0, CP360_ERR_BAD_ARG,
+                  "faces wider than 16 need an 8 B-aligned scratch buffer of B*2w*4w uint64");
   const int64_t n = B * 8 * (int64_t)w * w;
   CP360_CUDA_OK(cudaMemsetAsync(scratch, 0, (size_t)n * sizeof(uint64_t), st));   // below every key
   rc = launch_c2e<2>(cube, taps, wts, reinterpret_cast<float*>(scratch), B, C, w, st);
@@ -469,17 +993,21 @@ int cp360_c2e_max_arg_fwd(const float* cube, const uint32_t* taps, const float* 
   return CP360_OK;
 }
 
-int cp360_c2e_max_bwd(const float* gsal, const int32_t* argmax, const uint32_t* taps, const float* wts,
+int cp360_c2e_max_bwd(const float* gsal, const int32_t* argmax, const int32_t* offs, const int32_t* pix, const float* bwts,
                       float* gcube, int64_t B, int64_t C, int w, void* stream) {
-  int rc = check_common(gsal, taps, wts, gcube, B, C, w);
-  if (rc != CP360_OK || B == 0 || C == 0) return rc;
-  CP360_CHECK_ARG(argmax && ((uintptr_t)argmax % 4) == 0, CP360_ERR_BAD_ARG, "argmax null or misaligned");
+  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0 && w <= 8191 && C <= 0x7fffffff, CP360_ERR_BAD_ARG, "bad size");
+  if (B == 0 || C == 0) return CP360_OK;
+  CP360_CHECK_ARG(gsal && gcube && argmax, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG(((uintptr_t)gsal % 4) == 0 && ((uintptr_t)gcube % 4) == 0 && ((uintptr_t)argmax % 4) == 0, CP360_ERR_ALIGN,
+                  "tensors must be 4 B aligned");
+  int rc = check_bwd_plan(offs, pix, bwts);
+  if (rc != CP360_OK) return rc;
+  rc = require_device();
+  if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int P = 8 * w * w;
   CP360_CUDA_OK(cudaMemsetAsync(gcube, 0, (size_t)B * 6 * C * w * w * sizeof(float), st));
-  dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)std::min<int64_t>(B, 65535));
-  c2e_max_bwd_kernel<<<grid, kC2eThreads, 0, st>>>(gsal, argmax, taps, reinterpret_cast<const float4*>(wts),
-                                                   gcube, B, (int)C, w);
+  dim3 grid((6 * w * w + kC2eThreads - 1) / kC2eThreads, (unsigned)std::min<int64_t>(B, 65535));
+  c2e_max_bwd_gather_kernel<<<grid, kC2eThreads, 0, st>>>(gsal, argmax, offs, pix, bwts, gcube, B, (int)C, w);
   CP360_LAUNCHED();
   return CP360_OK;
 }
@@ -496,6 +1024,18 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
   if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = 8 * w * w;
+  static const bool lanech = [] { const char* v = getenv("CP360_CUBIC_LANECH"); return !(v && *v == '0'); }();
+  if (w <= 8 && lanech) {                               // lane = channel kernel (any alignment, any C)
+    const int ww = w * w, S = ww | 1;
+    const int64_t groups = (C + 31) / 32;
+    CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
+    const size_t smem_l = (size_t)((6 * 32 * S + 3) & ~3) * 4 + (size_t)P * 64 + (size_t)32 * (kCubicTilePix + 1) * 4;
+    CP360_CUDA_OK(cudaFuncSetAttribute(c2e_cubic_lanech_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+    launch_kernel(c2e_cubic_lanech_kernel, (unsigned)(B * groups), kCubicLaneThreads, smem_l, st, cube, taps, equi,
+                  (int)C, w, (int)groups);
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
   size_t smem = 0;
   int k = small_plan(cube, C, w, &smem);
   if (k > 0) {
@@ -521,19 +1061,28 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
   return CP360_OK;
 }
 
-int cp360_c2e_bwd(const float* gequi, const uint32_t* taps, const float* wts, float* gcube,
+int cp360_c2e_bwd(const float* gequi, const int32_t* offs, const int32_t* pix, const float* bwts, float* gcube,
                   int64_t B, int64_t C, int w, void* stream) {
-  int rc = check_common(gequi, taps, wts, gcube, B, C, w);
-  if (rc != CP360_OK || B == 0 || C == 0) return rc;
+  CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0 && w <= 8191 && C <= 0x7fffffff, CP360_ERR_BAD_ARG, "bad size");
+  if (B == 0 || C == 0) return CP360_OK;
+  CP360_CHECK_ARG(gequi && gcube, CP360_ERR_BAD_ARG, "null pointer");
+  CP360_CHECK_ARG(((uintptr_t)gequi % 4) == 0 && ((uintptr_t)gcube % 4) == 0, CP360_ERR_ALIGN, "tensors must be 4 B aligned");
+  int rc = check_bwd_plan(offs, pix, bwts);
+  if (rc != CP360_OK) return rc;
+  rc = require_device();
+  if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = 8 * w * w;
-  CP360_CUDA_OK(cudaMemsetAsync(gcube, 0, (size_t)B * 6 * C * w * w * sizeof(float), st));
-  const int chb = (int)std::min<int64_t>(16, C);
-  dim3 grid((P + kC2eThreads - 1) / kC2eThreads, (unsigned)((C + chb - 1) / chb),
-            (unsigned)std::min<int64_t>(B, 65535));
-  CP360_CHECK_ARG(grid.y <= 65535, CP360_ERR_RANGE, "too many channel chunks");
-  c2e_bwd_kernel<<<grid, kC2eThreads, 0, st>>>(gequi, taps, reinterpret_cast<const float4*>(wts),
-                                               gcube, B, (int)C, w, chb);
+  // channel group: 16 (8 at w = 16) gradient planes staged in shared memory for small faces, 8 read in place otherwise
+  const bool small = w <= 16 && ((uintptr_t)gequi % 16) == 0 && (P % 4) == 0;
+  const int kch = (small && w <= 8) ? 16 : 8;
+  const int64_t groups = (C + kch - 1) / kch;
+  CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
+  const size_t smem = small ? 128 + (size_t)kch * P * 4 : 0;
+  void (*kern)(const float*, const int32_t*, const int32_t*, const float*, float*, int, int, int) =
+      small ? (kch == 16 ? c2e_bwd_gather_kernel<16, true> : c2e_bwd_gather_kernel<8, true>) : c2e_bwd_gather_kernel<8, false>;
+  if (small) CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(B * groups), kC2eSmallThreads, smem, st>>>(gequi, offs, pix, bwts, gcube, (int)C, w, (int)groups);
   CP360_LAUNCHED();
   return CP360_OK;
 }

@@ -597,7 +597,7 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   }
 #undef CP360_CUBE_K
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int cons_warps = std::min(31, std::max(1, knob("CP360_CUBE_WARPS", t_tune ? t_tune->cube_warps : 0, 16)));
+  const int cons_warps = std::min(kCubeMaxConsWarps, std::max(1, knob("CP360_CUBE_WARPS", t_tune ? t_tune->cube_warps : 0, 16)));
   a.work = acquire_work_counter(st);
   // every CTA should own at least ~2 chunks
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count() * per_sm));
@@ -661,7 +661,7 @@ static int launch_cube_bwd(CubeBwdArgs a, size_t smem, const CubePadGeom& g, cud
     default: kern = cubepad_bwd_cube_kernel<0>; break;
   }
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int cons_warps = std::min(31, std::max(1, env_int("CP360_BWD_WARPS", 16)));
+  const int cons_warps = std::min(kCubeMaxConsWarps, std::max(1, env_int("CP360_BWD_WARPS", 16)));
   a.work = acquire_work_counter(st);
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count()));
   launch_kernel(kern, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);

@@ -40,7 +40,7 @@ struct CubeBwdArgs {
 
 // TK > 0: kmax known at compile time (the channel walk of a full chunk is unrolled in batches of 8)
 template <int TK>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kCubeMaxThreads, 1)
 cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [stages]
@@ -62,10 +62,14 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       tma::mbar_init(&full[s], 1);
-#ifdef CP360_ARRIVE_ALL
-      tma::mbar_init(&empty[s], n_cons);               // diagnostic build: every consumer thread arrives (tools/racecheck_probe.py)
-#else
+      // every consumer THREAD arrives on empty[s] (CP360_ARRIVE_PER_WARP: one lane per warp after __syncwarp —
+      // equally correct under the PTX memory model and equally fast on B200 (profiles/README.md §racecheck),
+      // but compute-sanitizer's racecheck only credits a barrier to the threads that arrive on it, so the
+      // per-thread form is the one that verifies clean)
+#ifdef CP360_ARRIVE_PER_WARP
       tma::mbar_init(&empty[s], n_cons_warps);
+#else
+      tma::mbar_init(&empty[s], n_cons);
 #endif
     }
     tma::fence_mbar_init();
@@ -210,11 +214,11 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
         }
       }
     }
-#ifdef CP360_ARRIVE_ALL
-    tma::mbar_arrive(&empty[s]);
-#else
+#ifdef CP360_ARRIVE_PER_WARP
     __syncwarp();                                      // orders every lane's reads of the stage before lane 0's release
     if (lane == 0) tma::mbar_arrive(&empty[s]);
+#else
+    tma::mbar_arrive(&empty[s]);                       // release: this thread's reads of the stage are done
 #endif
     if (++s == a.stages) { s = 0; ph ^= 1u; }
   }

@@ -25,6 +25,8 @@
 namespace cp360 {
 
 constexpr int kCubeMaxStages = 8;
+constexpr int kCubeMaxConsWarps = 16;                        // + the producer warp: 544 threads, up to 120 registers each
+constexpr int kCubeMaxThreads = 32 * (kCubeMaxConsWarps + 1);
 
 struct Cube2Args {
   const uint32_t* x;
@@ -49,7 +51,7 @@ struct Cube2Args {
 // time — plane strides become immediates and the channel walk of a full chunk is unrolled, one LDS
 // and one STG per word. TH == 0 / TK == 0: run-time geometry / chunk depth.
 template <int TH, int TP, int TK, bool EPI>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kCubeMaxThreads, 1)
 cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [stages]
@@ -71,11 +73,15 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
   CP360_TRACE_INIT_MIN(2);
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      tma::mbar_init(&full[s], 1);
-#ifdef CP360_ARRIVE_ALL
-      tma::mbar_init(&empty[s], n_cons);               // diagnostic build: every consumer thread arrives (tools/racecheck_probe.py)
-#else
+      tma::mbar_init(&full[s], EPI ? 32 : 1);          // EPI: every producer lane releases its scale/shift writes itself
+      // every consumer THREAD arrives on empty[s] (CP360_ARRIVE_PER_WARP: one lane per warp after __syncwarp —
+      // equally correct under the PTX memory model and equally fast on B200 (profiles/README.md §racecheck),
+      // but compute-sanitizer's racecheck only credits a barrier to the threads that arrive on it, so the
+      // per-thread form is the one that verifies clean)
+#ifdef CP360_ARRIVE_PER_WARP
       tma::mbar_init(&empty[s], n_cons_warps);
+#else
+      tma::mbar_init(&empty[s], n_cons);
 #endif
     }
     tma::fence_mbar_init();
@@ -105,23 +111,19 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
     uint32_t ticket = blockIdx.x;
     for (int64_t it = 0;; ++it) {
       int64_t q = 0;
+      if (EPI && it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);   // every lane acquires the slot it is about to write
       if (lane == 0) {
-        if (it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
+        if (!EPI && it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
         q = (int64_t)blockIdx.x + it * gridDim.x;
         if (a.work) {
           q = (int64_t)ticket;
           if (q < a.n_chunks) ticket = gridDim.x + atomicAdd(a.work, 1u);
         }
       }
-      if (EPI) {
-        __syncwarp();                                  // lane 0's acquire of empty[s] orders the slot writes below
-        q = __shfl_sync(0xffffffffu, q, 0);
-      }
+      if (EPI) q = __shfl_sync(0xffffffffu, q, 0);
       if (q >= a.n_chunks) {
-        if (lane == 0) {
-          chunk_of[s] = -1;
-          tma::mbar_arrive(&full[s]);                  // completes the phase: consumers see the end mark
-        }
+        if (lane == 0) chunk_of[s] = -1;
+        if (EPI || lane == 0) tma::mbar_arrive(&full[s]);   // completes the phase: consumers see the end mark
         break;
       }
       const int64_t n = q / a.cblocks;
@@ -133,7 +135,7 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
           es[i] = a.scale ? __ldg(a.scale + c0 + i) : 1.0f;
           es[kmax + i] = a.shift ? __ldg(a.shift + c0 + i) : 0.0f;
         }
-        __syncwarp();                                  // ... and the slot writes precede lane 0's release on full[s]
+        if (lane != 0) tma::mbar_arrive(&full[s]);     // release of this lane's slot writes (lane 0: expect_tx below)
       }
       if (lane == 0) {
         chunk_of[s] = q;
@@ -237,11 +239,11 @@ cubepad_cube2_kernel(const Cube2Args a, const __grid_constant__ CubePadGeom g) {
         for (; cc < kl; ++cc, sp += HW, dp += HoWo) __stcs(dp, EPI ? epi(*sp, cc) : *sp);
       }
     }
-#ifdef CP360_ARRIVE_ALL
-    tma::mbar_arrive(&empty[s]);
-#else
+#ifdef CP360_ARRIVE_PER_WARP
     __syncwarp();                                      // orders every lane's reads of the stage before lane 0's release
     if (lane == 0) tma::mbar_arrive(&empty[s]);
+#else
+    tma::mbar_arrive(&empty[s]);                       // release: this thread's reads of the stage are done
 #endif
     if (++s == a.stages) { s = 0; ph ^= 1u; }
   }

@@ -184,7 +184,9 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
 }
 
 template <int NJ, bool FULL, bool EPI>
-__global__ void __launch_bounds__(kRowThreads)
+// one 8-warp CTA per SM (two at most): registers are plentiful — tell ptxas, which otherwise holds the kernel at 64
+// registers for occupancy it cannot use and spills inside the copy loops
+__global__ void __launch_bounds__(kRowThreads, 1)
 cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

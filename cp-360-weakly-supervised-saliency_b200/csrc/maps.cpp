@@ -253,6 +253,40 @@ int cp360_c2e_build_plan(int w, int align_corners, uint32_t* tap_host, float* wt
   return CP360_OK;
 }
 
+int cp360_c2e_build_bwd_plan(int w, int align_corners, int32_t* offsets_host, int32_t* pix_host, float* wts_host) {
+  if (w <= 0 || !offsets_host) { set_error("c2e backward plan: bad argument"); return CP360_ERR_BAD_ARG; }
+  if (w > 8191) { set_error("c2e backward plan: face width > 8191"); return CP360_ERR_RANGE; }
+  const size_t P = (size_t)8 * w * w, NC = (size_t)6 * w * w;
+  std::vector<uint32_t> tap(P);
+  std::vector<float> wts(4 * P);
+  int rc = cp360_c2e_build_plan(w, align_corners, tap.data(), wts.data(), nullptr);
+  if (rc != CP360_OK) return rc;
+  // the four taps of output pixel i, in the order the forward kernel accumulates them (nw, ne, sw, se)
+  auto for_each_tap = [&](size_t i, auto&& fn) {
+    const int face = (int)(tap[i] >> 28), y0 = (int)((tap[i] >> 14) & 0x3fffu) - 1, x0 = (int)(tap[i] & 0x3fffu) - 1;
+    const int dy[4] = {0, 0, 1, 1}, dx[4] = {0, 1, 0, 1};
+    for (int k = 0; k < 4; ++k) {
+      const int yy = y0 + dy[k], xx = x0 + dx[k];
+      if (yy < 0 || yy >= w || xx < 0 || xx >= w) continue;      // padding_mode='zeros': no gradient
+      fn(((size_t)face * w + yy) * w + xx, wts[4 * i + k]);
+    }
+  };
+  std::vector<int32_t> count(NC + 1, 0);
+  for (size_t i = 0; i < P; ++i) for_each_tap(i, [&](size_t cell, float) { ++count[cell + 1]; });
+  for (size_t c = 0; c < NC; ++c) count[c + 1] += count[c];
+  for (size_t c = 0; c <= NC; ++c) offsets_host[c] = count[c];
+  if (pix_host && wts_host) {
+    std::vector<int32_t> fill(count.begin(), count.end() - 1);
+    for (size_t i = 0; i < P; ++i)                               // increasing output pixel: the fixed summation order
+      for_each_tap(i, [&](size_t cell, float wt) {
+        pix_host[fill[cell]] = (int32_t)i;
+        wts_host[fill[cell]] = wt;
+        ++fill[cell];
+      });
+  }
+  return CP360_OK;
+}
+
 int cp360_c2e_build_cubic_plan(int w, uint32_t* tap_host) {
   if (w <= 0 || !tap_host) { set_error("c2e cubic plan: bad argument"); return CP360_ERR_BAD_ARG; }
   if (w > 512) { set_error("c2e cubic plan: face width > 512"); return CP360_ERR_RANGE; }

@@ -42,6 +42,22 @@ class Cube2Equi:
             self._plan_dev[key] = p
         return p
 
+    def _bwd_plan_on(self, device):
+        """Transposed plan (cp360_c2e_build_bwd_plan) on `device`: (offsets, pixels, weights)."""
+        key = ("bwd", device.type, device.index)
+        p = self._plan_dev.get(key)
+        if p is None:
+            w = self.input_w
+            offs = np.empty(6 * w * w + 1, dtype=np.int32)
+            lib = _lib.lib()
+            _lib.check(lib.cp360_c2e_build_bwd_plan(w, int(self.align_corners), offs.ctypes.data, None, None))
+            n = int(offs[-1])
+            pix, wts = np.empty(max(n, 1), dtype=np.int32), np.empty(max(n, 1), dtype=np.float32)
+            _lib.check(lib.cp360_c2e_build_bwd_plan(w, int(self.align_corners), offs.ctypes.data, pix.ctypes.data, wts.ctypes.data))
+            p = tuple(torch.from_numpy(a).to(device) for a in (offs, pix, wts))
+            self._plan_dev[key] = p
+        return p
+
     def _prepare(self, input_data):
         if isinstance(input_data, np.ndarray):
             # dataset_feat_extractor.py:174 hands over a numpy array (SURVEY.md §3.1)
@@ -81,7 +97,12 @@ class Cube2Equi:
         b, c, w = gout.shape[0], gout.shape[1], self.input_w
         g = gout.float().contiguous()
         gx = torch.empty((6 * b, c, w, w), dtype=torch.float32, device=g.device)
-        return self._launch("cp360_c2e_bwd", g, gx, b, c)
+        offs, pix, wts = self._bwd_plan_on(g.device)
+        with torch.cuda.device(g.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().cp360_c2e_bwd(g.data_ptr(), offs.data_ptr(), pix.data_ptr(), wts.data_ptr(), gx.data_ptr(),
+                                                b, c, w, st))
+        return gx
 
     def to_equi_max(self, input_data, out=None):
         """Fused back-projection + channel max: [6B,C,w,w] -> [B,2w,4w]
@@ -103,24 +124,24 @@ class Cube2Equi:
         b, c, w = x.shape[0] // 6, x.shape[1], self.input_w
         sal = torch.empty((b, 2 * w, 4 * w), dtype=torch.float32, device=x.device)
         arg = torch.empty((b, 2 * w, 4 * w), dtype=torch.int32, device=x.device)
-        scratch = torch.empty((b, 2 * w, 4 * w), dtype=torch.int64, device=x.device)
+        scratch = torch.empty((b, 2 * w, 4 * w), dtype=torch.int64, device=x.device) if w > 16 else None
         taps, wts = self._plan_on(x.device)
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().cp360_c2e_max_arg_fwd(
                 x.data_ptr(), taps.data_ptr(), wts.data_ptr(), sal.data_ptr(), arg.data_ptr(),
-                scratch.data_ptr(), b, c, w, st))
+                scratch.data_ptr() if scratch is not None else None, b, c, w, st))
         return sal, arg
 
     def _max_backward(self, gsal, arg, c):
         b, w = gsal.shape[0], self.input_w
         g = gsal.float().contiguous()
         gx = torch.empty((6 * b, c, w, w), dtype=torch.float32, device=g.device)
-        taps, wts = self._plan_on(g.device)
+        offs, pix, wts = self._bwd_plan_on(g.device)
         with torch.cuda.device(g.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().cp360_c2e_max_bwd(
-                g.data_ptr(), arg.data_ptr(), taps.data_ptr(), wts.data_ptr(), gx.data_ptr(), b, c, w, st))
+                g.data_ptr(), arg.data_ptr(), offs.data_ptr(), pix.data_ptr(), wts.data_ptr(), gx.data_ptr(), b, c, w, st))
         return gx
 
     def _cubic_plan_on(self, device):

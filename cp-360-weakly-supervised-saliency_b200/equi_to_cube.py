@@ -145,7 +145,8 @@ class Equi2Cube:
         """in_image ndarray [H,W,C] -> {0..5: ndarray[w,w,C] of in_image.dtype} (equi_to_cube.py:112-129).
 
         The GPU path computes in float32 (the BASELINE configuration); float64 input is rounded
-        to float32 first, so results agree with the reference's float64 run to ~1e-7."""
+        to float32 first, so results agree with the reference's float64 run to ~1e-7. Integer input is
+        rounded to nearest and saturated on the way back (cv2 semantics to within 1 LSB)."""
         dev = self._pick_device()
         if isinstance(in_image, torch.Tensor):
             src, np_dtype = in_image, None
@@ -158,5 +159,13 @@ class Equi2Cube:
         faces = self.to_cube_tensor(src.to(dev, non_blocking=True), layout="NHWC")
         if np_dtype is None:
             return {i: faces[i] for i in range(6)}
-        host = faces.cpu().numpy().astype(np_dtype, copy=False)
+        host = faces.cpu().numpy()
+        if np.issubdtype(np_dtype, np.integer):
+            # integer frames (e.g. uint8): resampled in float32, then rounded to nearest and saturated like
+            # cv2's saturate_cast — within 1 LSB of cv2.remap's own 8-bit fixed-point path (pinned by
+            # tests/test_oracle_golden.py::test_e2c_integer_frames_within_one_lsb_of_cv2); the reference itself
+            # only ever passes float frames (dataset_feat_extractor.py:131,142)
+            info = np.iinfo(np_dtype)
+            host = np.clip(np.rint(host), info.min, info.max)
+        host = host.astype(np_dtype, copy=False)
         return {i: host[i] for i in range(6)}

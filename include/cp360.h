@@ -212,23 +212,36 @@ CP360_API int cp360_c2e_fwd(const float* cube_dev, const uint32_t* tap_dev, cons
 
 /* Device, fp32: sal[B,2w,4w] = max over channels of the above, without materialising it
  * (test_temporal.py:82-84, train_temporal.py:105-106, dataset_feat_extractor.py:174-175).
- * NaNs are ignored by the max (torch.max would propagate them). */
+ * NaN semantics are torch.max's: a NaN in any channel of a pixel makes that pixel NaN.
+ * w <= 16: one kernel, no atomics — a thread-block cluster per frame splits the channels, the partial maps meet in
+ * distributed shared memory and are combined with warp shuffles; bit-reproducible. Larger faces: a -inf fill
+ * plus an order-preserving atomic max. */
 CP360_API int cp360_c2e_max_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
                       float* sal_dev, int64_t B, int64_t C, int w, void* stream);
 
 /* Device, fp32: the same channel max together with the channel it came from — the differentiable
  * form the training path needs (train_temporal.py:105-107 backprops through to_equi_nn + torch.max):
- * sal[B,2w,4w], argmax[B,2w,4w] int32 (lowest channel among equal maxima, as torch.max(dim)).
- * scratch: caller-owned uint64[B*2w*4w] work buffer (overwritten). */
+ * sal[B,2w,4w], argmax[B,2w,4w] int32 (lowest channel among equal maxima, the first NaN channel if any, as
+ * torch.max(dim)). scratch: caller-owned uint64[B*2w*4w] work buffer, needed (and overwritten) only for
+ * w > 16; may be NULL for smaller faces. */
 CP360_API int cp360_c2e_max_arg_fwd(const float* cube_dev, const uint32_t* tap_dev, const float* wts_dev,
                           float* sal_dev, int32_t* argmax_dev, uint64_t* scratch_dev, int64_t B, int64_t C,
                           int w, void* stream);
 
+/* Host: the TRANSPOSE of the sampling plan, for the backward passes: for cube pixel s = (face*w + y)*w + x,
+ * entries [offsets_host[s], offsets_host[s+1]) list the equirect pixels that sample it (pix_host, increasing) and
+ * the bilinear weight each applies (wts_host). offsets_host[6*w*w + 1]; pix_host / wts_host hold
+ * offsets_host[6*w*w] <= 32*w*w entries (pass NULL for both to only count). */
+CP360_API int cp360_c2e_build_bwd_plan(int w, int align_corners, int32_t* offsets_host, int32_t* pix_host,
+                             float* wts_host);
+
 /* Device, fp32: backward of the fused channel max: gcube[6B,C,w,w] (zero-filled here) receives
  * gsal[b,pix] * weight at the four taps of channel argmax[b,pix] — what autograd yields for
- * torch.max(to_equi_nn(x), 1)[0] without materialising the [B,C,2w,4w] map or its gradient. */
-CP360_API int cp360_c2e_max_bwd(const float* gsal_dev, const int32_t* argmax_dev, const uint32_t* tap_dev,
-                      const float* wts_dev, float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
+ * torch.max(to_equi_nn(x), 1)[0] without materialising the [B,C,2w,4w] map or its gradient. Gather over the
+ * transposed plan (cp360_c2e_build_bwd_plan, device copies): no atomics, fixed summation order. */
+CP360_API int cp360_c2e_max_bwd(const float* gsal_dev, const int32_t* argmax_dev, const int32_t* offsets_dev,
+                      const int32_t* pix_dev, const float* bwts_dev, float* gcube_dev, int64_t B, int64_t C, int w,
+                      void* stream);
 
 /* Host: sampling plan of Cube2Equi.to_equi_cv2, cube_to_equi.py:68-91 — cv2.remap(INTER_CUBIC) fed
  * float32(out_coord) as it is (face pixels, no normalisation): s = cvRound(float32(coord)*32),
@@ -244,9 +257,12 @@ CP360_API int cp360_c2e_build_cubic_plan(int w, uint32_t* tap_host);
 CP360_API int cp360_c2e_cubic_fwd(const float* cube_dev, const uint32_t* tap_dev, float* equi_dev, int64_t B,
                         int64_t C, int w, void* stream);
 
-/* Device, fp32: gcube[6B,C,w,w] = d(c2e)^T(gequi[B,C,2w,4w]) (bilinear scatter-add). */
-CP360_API int cp360_c2e_bwd(const float* gequi_dev, const uint32_t* tap_dev, const float* wts_dev,
-                  float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
+/* Device, fp32: gcube[6B,C,w,w] = d(c2e)^T(gequi[B,C,2w,4w]) — the gradient of cp360_c2e_fwd
+ * (train_temporal.py:167-170 back-propagates through to_equi_nn). A gather over the transposed plan
+ * (cp360_c2e_build_bwd_plan, device copies): every cube pixel sums its contributors in a fixed order, no
+ * atomics — bit-reproducible, and gcube needs no zero fill. */
+CP360_API int cp360_c2e_bwd(const float* gequi_dev, const int32_t* offsets_dev, const int32_t* pix_dev,
+                  const float* bwts_dev, float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * .npy files either side of the path: cube score files `cube_feat/%06d.npy` [6,1000,7,7]

@@ -632,11 +632,15 @@ def test_c2e_numpy_input_and_errors(dev):
         c2e.to_equi_nn(torch.zeros(6, 3, 7, 7))
 
 
-def test_c2e_vs_torch_grid_sample(dev):
-    """The reference's own formulation (cube_to_equi.py:58-65) executed with torch CUDA ops."""
+@pytest.mark.parametrize("align", [False, True])
+def test_c2e_vs_torch_grid_sample(dev, align):
+    """The reference's own formulation (cube_to_equi.py:58-65) executed with torch CUDA ops, in both grid_sample
+    conventions: align_corners=False (what the unmodified call computes under the installed torch — the default here)
+    and align_corners=True (what it computed under the torch <= 1.2 the reference was written for). Also through
+    SphericalPipeline / SaliencyHead, which take the flag."""
     import torch.nn.functional as F
     for w, C in [(8, 64), (16, 8), (7, 33)]:
-        c2e = cp360_b200.Cube2Equi(w)
+        c2e = cp360_b200.Cube2Equi(w, align_corners=align)
         x = torch.randn(6, C, w, w, device=dev)
         g = torch.from_numpy(c2e.out_coord.astype(np.float32)).to(dev)
         fm = torch.from_numpy(c2e.face_map.astype(np.int64)).to(dev)
@@ -644,12 +648,16 @@ def test_c2e_vs_torch_grid_sample(dev):
         gn = ((g - M / 2) / (M / 2))[None]
         want = torch.zeros(1, C, 2 * w, 4 * w, device=dev)
         for f in range(6):
-            s = F.grid_sample(x[f:f + 1], gn, mode="bilinear", padding_mode="zeros", align_corners=False)
+            s = F.grid_sample(x[f:f + 1], gn, mode="bilinear", padding_mode="zeros", align_corners=align)
             m = (fm == f)[None, None].expand_as(want)
             want[m] = s[m]
         got = c2e.to_equi_nn(x)
         assert (got - want).abs().max().item() <= C2E_TOL
         assert (c2e.to_equi_max(x) - want.max(1)[0]).abs().max().item() <= C2E_TOL
+    pipe = cp360_b200.SphericalPipeline(96, 192, 32, 16, 32, device=dev, align_corners=align)
+    assert pipe.c2e.align_corners == align
+    head = cp360_b200.SaliencyHead(torch.randn(10, 8), 7, align_corners=align)
+    assert head.c2e.align_corners == align
 
 
 def test_c2e_backward_matches_autograd(dev):
@@ -714,6 +722,54 @@ def test_c2e_max_ties_pick_lowest_channel(dev):
     pos = (full[:, 7] > full[:, 0])                       # pixels whose taps are not all zero-weighted
     assert torch.equal(arg[pos], torch.full_like(arg[pos], 7))
     assert int(arg.min().item()) >= 0 and int(arg.max().item()) < 40
+
+
+@pytest.mark.parametrize("w,C,B", [(8, 1000, 3), (7, 1000, 2), (16, 64, 2), (8, 24, 40), (24, 16, 2)])
+def test_c2e_max_nan_semantics_match_torch_max(dev, w, C, B):
+    """torch.max (test_temporal.py:83) propagates NaN: a pixel whose taps reach a NaN in ANY channel is NaN, and
+    torch.max(dim) reports the first NaN channel. The fused kernels (cluster kernel for w <= 16, atomic path above)
+    must agree with torch.max of the materialised map, values and indices, +-inf included."""
+    torch.manual_seed(w * 1000 + C)
+    c2e = cp360_b200.Cube2Equi(w)
+    x = torch.randn((6 * B, C, w, w), device=dev)
+    x[0, C // 2, w // 2, w // 2] = float("nan")            # frame 0: one NaN in the Back face
+    x[2, 3, 1, 1] = float("nan")                           #          and an earlier-channel NaN in the Front face
+    x[2, C - 1, 1, 1] = float("nan")
+    if B > 1:
+        x[6 + 5, 0, :, :] = float("inf")                   # frame 1: +inf plane (0 * inf taps must not create NaNs off-face)
+        x[6 + 1, 1, 0, 0] = float("-inf")
+    full = c2e.to_equi_nn(x)
+    want_v, want_i = torch.max(full, 1)
+    sal = c2e.to_equi_max(x)
+    sal2, arg = c2e.to_equi_max_with_indices(x)
+    assert torch.isnan(want_v).any() and not torch.isnan(want_v).all()
+    n_want = int(torch.isnan(want_v).sum())
+    for tag, got in (("max", sal), ("max+arg", sal2)):
+        bad = torch.isnan(got) != torch.isnan(want_v)
+        assert not bool(bad.any()), "%s: NaN pattern differs at %d pixels (want %d NaNs, got %d); first: %s got %s want %s" % (
+            tag, int(bad.sum()), n_want, int(torch.isnan(got).sum()), bad.nonzero()[0].tolist(),
+            got[bad][0].item(), want_v[bad][0].item())
+    ok = ~torch.isnan(want_v)
+    assert torch.equal(sal[ok], want_v[ok]) and torch.equal(sal2[ok], want_v[ok])
+    assert torch.equal(arg.long(), want_i), "arg-max channel differs from torch.max (first maximal / first NaN index)"
+
+
+def test_c2e_fused_max_and_backward_are_bit_reproducible(dev):
+    """No atomics anywhere on the small-face path: forward max, full backward and routed max-backward give the
+    same bits on every run."""
+    torch.manual_seed(5)
+    c2e = cp360_b200.Cube2Equi(8)
+    x = torch.randn((6 * 7, 1000, 8, 8), device=dev)
+    g = torch.randn((7, 1000, 16, 32), device=dev)
+    gs = torch.randn((7, 16, 32), device=dev)
+    sal0, arg0 = c2e.to_equi_max_with_indices(x)
+    b0 = c2e._backward(g)
+    m0 = c2e._max_backward(gs, arg0, 1000)
+    for _ in range(3):
+        sal, arg = c2e.to_equi_max_with_indices(x)
+        assert torch.equal(sal, sal0) and torch.equal(arg, arg0) and torch.equal(c2e.to_equi_max(x), sal0)
+        assert torch.equal(c2e._backward(g), b0)
+        assert torch.equal(c2e._max_backward(gs, arg0, 1000), m0)
 
 
 def test_c2e_full_size_properties(dev):

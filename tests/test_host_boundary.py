@@ -104,8 +104,11 @@ def test_e2c_errors():
         cp360_b200.Equi2Cube(8, np.zeros((32, 60, 3), np.float32))          # equi_to_cube.py:15
     lib = _lib.lib()
     assert lib.cp360_e2c_build_map(8, 32, 60, 90.0, None, None, None, None, None) == 3
-    big = np.empty(6 * 4 * 4, np.uint32)
-    assert lib.cp360_e2c_build_map(4, 2048, 4096, 90.0, big.ctypes.data, None, None, None, None) == 4
+    # frames beyond 2047 x 1023 take the wide (two-word) map; only sizes beyond 65535 x 32767 are out of range
+    assert lib.cp360_e2c_map_words(4, 960, 1920) == 6 * 16 and lib.cp360_e2c_map_words(4, 2048, 4096) == 12 * 16
+    big = np.empty(12 * 4 * 4, np.uint32)
+    assert lib.cp360_e2c_build_map(4, 2048, 4096, 90.0, big.ctypes.data, None, None, None, None) == 0
+    assert lib.cp360_e2c_build_map(4, 40000, 80000, 90.0, None, None, None, None, None) == 4
     assert lib.cp360_e2c_fwd(None, None, None, 1, 32, 60, 3, 8, 0, None, None, None) == 3
 
 
@@ -176,3 +179,37 @@ def test_cubepad_inverse_map_is_transpose_of_forward_map(H, pad):
     offs2 = np.empty_like(offs)
     _lib.check(_lib.lib().cp360_cubepad_build_inverse_map(H, H, pl, pr, pt, pd, offs2.ctypes.data, None))
     np.testing.assert_array_equal(offs, offs2)
+
+
+@pytest.mark.parametrize("w,align", [(2, 0), (3, 1), (7, 0), (7, 1), (8, 0), (16, 0), (20, 1)])
+def test_c2e_backward_plan_is_transpose_of_forward_plan(w, align):
+    """cp360_c2e_build_bwd_plan: CSR over cube pixels of the same (equirect pixel, weight) pairs the forward plan
+    applies — checked as dense matrices, and its application against torch autograd of grid_sample-style sampling
+    (the gradient Cube2Equi.to_equi_nn needs, train_temporal.py:167-170)."""
+    lib = _lib.lib()
+    P, NC = 8 * w * w, 6 * w * w
+    taps = np.empty(P, np.uint32)
+    wts = np.empty((P, 4), np.float32)
+    _lib.check(lib.cp360_c2e_build_plan(w, align, taps.ctypes.data, wts.ctypes.data, None))
+    fwd = np.zeros((P, NC), np.float64)
+    for i in range(P):
+        face, y0, x0 = int(taps[i] >> 28), int((taps[i] >> 14) & 0x3fff) - 1, int(taps[i] & 0x3fff) - 1
+        for k, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+            yy, xx = y0 + dy, x0 + dx
+            if 0 <= yy < w and 0 <= xx < w:
+                fwd[i, (face * w + yy) * w + xx] += wts[i, k]
+    offs = np.empty(NC + 1, np.int32)
+    _lib.check(lib.cp360_c2e_build_bwd_plan(w, align, offs.ctypes.data, None, None))
+    n = int(offs[-1])
+    assert offs[0] == 0 and np.all(np.diff(offs) >= 0) and int((fwd != 0).sum()) <= n <= 4 * P
+    pix, bw = np.empty(n, np.int32), np.empty(n, np.float32)
+    _lib.check(lib.cp360_c2e_build_bwd_plan(w, align, offs.ctypes.data, pix.ctypes.data, bw.ctypes.data))
+    bwd = np.zeros((NC, P), np.float64)
+    for s in range(NC):
+        seg = pix[offs[s]:offs[s + 1]]
+        assert np.all(np.diff(seg) > 0), "contributors must be listed once each, in increasing order"
+        for e in range(offs[s], offs[s + 1]):
+            bwd[s, pix[e]] += bw[e]
+    np.testing.assert_array_equal(bwd, fwd.T)
+    # every equirect pixel's valid weights sum to <= 1 (bilinear), the plan has no entry for out-of-face taps
+    assert float(fwd.sum(axis=1).max()) <= 1.0 + 1e-6

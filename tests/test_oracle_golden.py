@@ -175,3 +175,24 @@ def test_ref_port_e2c_c2e(golden_meta, golden_small):
         out = port.to_equi_nn(torch.from_numpy(cube)).numpy()
         assert np.abs(out - golden_small[key + "_out"]).max() <= 4e-6, key
         np.testing.assert_array_equal(port.to_equi_max(torch.from_numpy(cube)).numpy(), out[0].max(axis=0))
+
+
+def test_e2c_integer_frames_within_one_lsb_of_cv2():
+    """Equi2Cube.to_cube on uint8 frames: the host mirror resamples in float32 and rounds to nearest + saturates
+    (equi_to_cube.py docstring). cv2.remap on 8-bit sources uses its own fixed-point path; pin how far the two
+    are apart on the same maps: never more than 1 LSB, equal on the large majority of pixels."""
+    import cv2
+    H, W, w = 96, 192, 24
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    inX, inY = oe2c.build_maps(w, H, W)
+    sx, sy = oe2c.fixed_maps(w, H, W)
+    faces = oe2c.to_cube(img.astype(np.float32), sx, sy).reshape(6, w, w, 3)
+    ours = np.clip(np.rint(faces), 0, 255).astype(np.uint8)
+    for f in range(6):
+        mx = inX[f].astype(np.float32).reshape(w, w)
+        my = inY[f].astype(np.float32).reshape(w, w)
+        want = np.stack([cv2.remap(np.ascontiguousarray(img[:, :, c]), mx, my, cv2.INTER_LINEAR) for c in range(3)], -1)
+        d = np.abs(ours[f].astype(np.int32) - want.astype(np.int32))
+        assert int(d.max()) <= 1
+        assert float((d == 0).mean()) > 0.9

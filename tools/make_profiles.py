@@ -22,7 +22,9 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
         "msecond": 1e3}
 # launches per step of each captured CubePad site in the benchmark chain (pipeline.resnet50_cubepad_sites(256) + 2048x8)
 SITE_COUNT = {"3_256_3": 1, "64_128_1": 1, "64_64_1": 3, "128_64_1": 1, "128_32_1": 3, "256_32_1": 1, "256_16_1": 5,
-              "512_16_1": 1, "512_8_1": 2, "2048_8_1": 1}
+              "512_16_1": 1, "512_8_1": 2, "2048_8_1": 1,
+              "3_224_3": 1, "64_112_1": 1, "64_56_1": 3, "128_56_1": 1, "128_28_1": 3, "256_28_1": 1, "256_14_1": 5,
+              "512_14_1": 1, "512_7_1": 2, "2048_7_1": 1, "2000_7_1": 0, "4000_7_1": 0}
 
 
 def raw(path):
@@ -79,8 +81,10 @@ def main(src, tag, batch=16, prof=None):
             us = num(rec, units, "gpu__time_duration.sum")
             lines.append("  => DRAM read+write %.1f MB in %.1f us = %.0f GB/s" % (dram / 1e6, us, dram / us / 1e3))
             cls = ("cubepad_row_kernel" if "row_kernel" in name else "cubepad_cube2_kernel" if "cube2" in name else
-                   "e2c_kernel" if "e2c" in name else "c2e_small_kernel<max> (+fill)" if "c2e" in name else name)
+                   "e2c_kernel" if "e2c" in name else "c2e_max_kernel" if "c2e" in name else name)
             n = SITE_COUNT.get(site, 1)
+            if n == 0:                              # captured for the record, not a launch of the benchmark chain
+                continue
             c = classes.setdefault(cls, [0.0, 0])
             c[0] += dram * n
             c[1] += n
@@ -88,11 +92,14 @@ def main(src, tag, batch=16, prof=None):
         f.write("\n".join(lines) + "\n")
     traffic = {k: int(v[0] / v[1]) for k, v in classes.items()}
     traffic["_frames_per_launch"] = batch
+    traffic["_cube"] = int(os.environ.get("CP360_PROF_CUBE", "256"))
+    traffic["_source"] = "ncu --set full, B=%d, profiles/%s_ncu_full.txt" % (batch, tag)
     traffic["_note"] = ("DRAM bytes (read+write) per launch from ncu --set full, averaged over the launches of the class in "
                         "one chain step at B=%d; isolated captures leave part of the output dirty in the 126 MB L2 at kernel "
                         "end, so writes are under-counted for sites whose output is < L2 (source: profiles/%s_ncu_full.txt)" % (batch, tag))
-    with open(os.path.join(prof, "traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    if os.environ.get("CP360_PROF_TRAFFIC", "1") != "0":
+        with open(os.path.join(prof, "traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     for a, b in (("bench.json", "%s_bench.json"), ("bench.err", "%s_bench_sites.txt"), ("kbench.txt", "%s_kbench.txt"),
                  ("launches.csv", "%s_launches.csv"), ("bench_reference.json", "%s_bench_reference.json"),
                  ("pytest_gpu.log", "%s_pytest_gpu.log"), ("smoke.log", "%s_smoke.log")):
