@@ -42,7 +42,7 @@ SIGNATURES = {
     "cp360_c2e_max_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
     "cp360_c2e_build_cubic_plan": (c_i32, [c_i32, c_vp]),
     "cp360_c2e_cubic_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
-    "cp360_c2e_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "cp360_c2e_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_i32, c_vp]),
     "cp360_host_alloc": (c_i32, [ctypes.c_uint64, c_i32, ctypes.POINTER(c_vp)]),
     "cp360_host_free": (c_i32, [c_vp]),
     "cp360_npy_read_header": (c_i32, [ctypes.c_char_p, ctypes.c_char_p, c_i32, p_i32, c_vp, c_i32, c_vp, p_i32]),

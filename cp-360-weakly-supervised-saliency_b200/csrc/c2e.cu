@@ -52,11 +52,12 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 // the LOWEST channel (torch.max(dim) returns the first maximal index). NaN is canonicalised to the quiet NaN
 // above +inf, so the first NaN channel wins, as in torch. Every key is > 0.
 __device__ __forceinline__ unsigned long long argmax_key(float v, int c) {
-  if (v != v) v = __int_as_float(0x7fc00000);
-  v += 0.0f;
-  const uint32_t b = __float_as_uint(v);
+  const uint32_t low = 0xffffffffu - (uint32_t)c;
+  if (v != v) return (0xffffffffull << 32) | low;            // above every number (no float arithmetic on the NaN)
+  uint32_t b = __float_as_uint(v);
+  if (b == 0x80000000u) b = 0u;                                // -0.0 -> +0.0
   const uint32_t o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-  return ((unsigned long long)o << 32) | (uint32_t)(0xffffffffu - (uint32_t)c);
+  return ((unsigned long long)o << 32) | low;
 }
 
 // running (max, arg-max) update with torch.max(dim) semantics: strictly greater replaces (first maximal index
@@ -367,186 +368,92 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
   cluster.sync();                                        // nobody exits while a neighbour may still read its partials
 }
 
-// ---- K3m for the reference's own map sizes (w <= 8): lane = channel, warp = output pixel ------------------------
-// With a thread per pixel (kernel above) the 32 lanes of every shared-memory load read the SAME 49- / 64-word channel
-// plane and collide in its banks; the kernel then sits on shared-memory bandwidth (measured: 1.7 TB/s of DRAM-side
-// bytes at [192,1000,8,8], ~2 wavefronts per load). Here the 32 lanes of a warp hold 32 CHANNELS of one pixel: the
-// channel planes are laid out with an ODD stride, so the four tap loads of a pixel are conflict-free, the pixel's
-// plan entry is a warp-uniform broadcast, and the channel max is a WARP-SHUFFLE reduction over the lanes
-// (north_star (c)), done once per pixel after the last stage — between stages every lane keeps its own running
-// max (and arg-max channel) for each of the warp's pixels in registers. Planes arrive through cp.async (4 B
-// granules: the padded layout cannot be a bulk copy) in a two-stage ring. Channel split across a cluster, DSMEM
-// combine and NaN semantics as in c2e_max_cluster_kernel. Any C, any alignment.
-constexpr int kLanechPixPerWarp = 32;         // 8 w^2 / 16 warps at w = 8
-constexpr int kLanechK = 32;                  // channels per stage = lanes
-
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tma::smem_addr(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int MODE>
-__global__ void __launch_bounds__(kC2eSmallThreads, 1)
-c2e_max_lanech_kernel(const C2eMaxArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int G = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
-  const int w = a.w, ww = w * w, P = 8 * ww, S = ww | 1;
-  float4* wt_s = reinterpret_cast<float4*>(smem_raw);                        // [P] bilinear weights nw, ne, sw, se
-  uint32_t* tap_s = reinterpret_cast<uint32_t*>(wt_s + P);                   // [P] face:3 | ok:4 | off3..off0 (6 bits each)
-  float* part_val = reinterpret_cast<float*>(tap_s + P);                     // [P]
-  int* part_arg = reinterpret_cast<int*>(part_val + P);                      // [P] (MODE 2)
-  float* ring = reinterpret_cast<float*>(smem_raw + a.ring_off);             // [2][6][32][S]
-  const int b = blockIdx.x / G;
-  const int c_begin = min(r * a.Cg, a.C), c_end = min(c_begin + a.Cg, a.C);
-  const int n_st = (c_end - c_begin + kLanechK - 1) / kLanechK;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float inv_ww = 1.0f / (float)ww;
-
-  pdl_trigger();
-  for (int pix = tid; pix < P; pix += kC2eSmallThreads) {                     // plan table (independent of the data)
-    const Tap t = decode_tap(__ldg(a.taps + pix));
-    const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
-    const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
-    const int xw = xw_ok ? t.x0 : 0, xe = xe_ok ? t.x0 + 1 : 0, yn = yn_ok ? t.y0 : 0, ys = ys_ok ? t.y0 + 1 : 0;
-    const uint32_t ok = (uint32_t)(xw_ok && yn_ok) | (uint32_t)(xe_ok && yn_ok) << 1 | (uint32_t)(xw_ok && ys_ok) << 2 |
-                        (uint32_t)(xe_ok && ys_ok) << 3;
-    tap_s[pix] = (uint32_t)t.face << 28 | ok << 24 | (uint32_t)(ys * w + xe) << 18 | (uint32_t)(ys * w + xw) << 12 |
-                 (uint32_t)(yn * w + xe) << 6 | (uint32_t)(yn * w + xw);
-    wt_s[pix] = __ldg(a.wts + pix);
-  }
-  pdl_wait();
-
-  auto issue = [&](int i) {                                                   // all threads: stage i -> ring[i & 1]
-    const int c0 = c_begin + i * kLanechK, kl = min(kLanechK, c_end - c0);
-    float* dst = ring + (size_t)(i & 1) * 6 * kLanechK * S;
-    const int n = kl * ww;
-    for (int f = 0; f < 6; ++f) {
-      const float* src = a.cube + (((int64_t)b * 6 + f) * a.C + c0) * ww;
-      float* df = dst + f * kLanechK * S;
-      for (int e = tid; e < n; e += kC2eSmallThreads) {
-        const int c = (int)(((float)e + 0.5f) * inv_ww);                      // e / ww, exact for these sizes
-        cp_async4(df + e + c * (S - ww), src + e);
-      }
-    }
-    cp_async_commit();
-  };
-
-  float best[kLanechPixPerWarp];
-  int best_c[MODE == 2 ? kLanechPixPerWarp : 1];
-#pragma unroll
-  for (int j = 0; j < kLanechPixPerWarp; ++j) {
-    best[j] = -INFINITY;
-    if (MODE == 2) best_c[j] = 0x7fffffff;
-  }
-  if (n_st > 0) issue(0);
-  for (int i = 0; i < n_st; ++i) {
-    if (i + 1 < n_st) { issue(i + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();                                                          // stage i is in place for every thread
-    const int c0 = c_begin + i * kLanechK, kl = min(kLanechK, c_end - c0);
-    const float* st = ring + (size_t)(i & 1) * 6 * kLanechK * S + lane * S;
-    const bool live = lane < kl;
-#pragma unroll
-    for (int j = 0; j < kLanechPixPerWarp; ++j) {
-      const int q = warp + j * (kC2eSmallThreads / 32);
-      if (q < P) {                                                            // warp-uniform
-        const uint32_t t = tap_s[q];
-        const float4 wt = wt_s[q];
-        const float* src = st + (t >> 28) * (kLanechK * S);
-        float acc = 0.0f;                      // order of torch's grid_sampler CUDA kernel
-        if (t & (1u << 24)) acc = fmaf(src[t & 63u], wt.x, acc);
-        if (t & (2u << 24)) acc = fmaf(src[(t >> 6) & 63u], wt.y, acc);
-        if (t & (4u << 24)) acc = fmaf(src[(t >> 12) & 63u], wt.z, acc);
-        if (t & (8u << 24)) acc = fmaf(src[(t >> 18) & 63u], wt.w, acc);
-        if (live) {
-          if (MODE == 1) best[j] = max_nan(best[j], acc);
-          else max_update(acc, c0 + lane, best[j], best_c[j]);
-        }
-      }
-    }
-    __syncthreads();                                                          // ring[i & 1] may be refilled (stage i + 2)
-  }
-  // channel max over the 32 lanes: warp shuffles; lane 0 publishes the CTA's partial
-#pragma unroll
-  for (int j = 0; j < kLanechPixPerWarp; ++j) {
-    const int q = warp + j * (kC2eSmallThreads / 32);
-    if (q < P) {
-      float v = best[j];
-      int vc = MODE == 2 ? best_c[j] : 0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, d);
-        if (MODE == 2) {
-          const int oc = __shfl_xor_sync(0xffffffffu, vc, d);
-          if (pair_better(ov, oc, v, vc)) { v = ov; vc = oc; }
-        } else {
-          v = max_nan(v, ov);
-        }
-      }
-      if (lane == 0) {
-        part_val[q] = v;
-        if (MODE == 2) part_arg[q] = vc;
-      }
-    }
-  }
-  cluster.sync();                                        // all G partial maps are in place (release / acquire)
-  const int Pr = (P + G - 1) / G;
-  for (int q0 = 0; q0 < Pr * G; q0 += kC2eSmallThreads) {       // warp-uniform trip count: every lane shuffles
-    const int q = q0 + tid;
-    const int j = q % G, pix = r * Pr + q / G;
-    const bool live = q < Pr * G && pix < P;
-    float v = -INFINITY;
-    int vc = 0x7fffffff;
-    if (live) {
-      v = *cluster.map_shared_rank(part_val + pix, j);
-      if (MODE == 2) vc = *cluster.map_shared_rank(part_arg + pix, j);
-    }
-    for (int d = G >> 1; d > 0; d >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, v, d);
-      if (MODE == 2) {
-        const int oc = __shfl_xor_sync(0xffffffffu, vc, d);
-        if (pair_better(ov, oc, v, vc)) { v = ov; vc = oc; }
-      } else {
-        v = max_nan(v, ov);
-      }
-    }
-    if (j == 0 && live) {
-      a.sal[(int64_t)b * P + pix] = v;
-      if (MODE == 2) a.arg[(int64_t)b * P + pix] = vc;
-    }
-  }
-  cluster.sync();                                        // nobody exits while a neighbour may still read its partials
-}
-
 // ---- backward of c2e as a GATHER over the transposed plan (cp360_c2e_build_bwd_plan): no atomics, fixed
-// summation order -> bit-reproducible gradients. Block = (frame, channel group); a thread owns cube pixels and
-// walks its contributors once, accumulating KCH channels in registers. SMALL: the gradient planes of the group
-// are staged in shared memory by one bulk copy (w <= 16), else they are read through the read-only path.
-template <int KCH, bool SMALL>
+// summation order -> bit-reproducible gradients. A thread owns cube pixels and walks its contributors once,
+// accumulating KCH channels in registers.
+//   c2e_bwd_small_kernel  w <= 16: CTA r of a frame walks the channel groups r, r + G, ...; the transposed plan is
+//                         copied to shared memory once per CTA (16-bit offsets / pixel ids), the gradient planes of
+//                         a group arrive by one TMA bulk copy each into a two-stage ring.
+//   c2e_bwd_gather_kernel any w: contributors and gradients read through the read-only path.
+struct C2eBwdArgs {
+  const float* gequi;
+  const int32_t* offs;
+  const int32_t* pix;
+  const float* wts;
+  float* gcube;
+  int C, w, G, n_entries;
+  int pix_off, wts_off, ring_off;      // byte offsets in dynamic shared memory (offs at 64)
+};
+
+template <int KCH>
+__global__ void __launch_bounds__(kC2eSmallThreads)
+c2e_bwd_small_kernel(const C2eBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                  // [2]
+  uint16_t* offs_s = reinterpret_cast<uint16_t*>(smem_raw + 64);           // [NC + 1]
+  uint16_t* pix_s = reinterpret_cast<uint16_t*>(smem_raw + a.pix_off);     // [n_entries]
+  float* wts_s = reinterpret_cast<float*>(smem_raw + a.wts_off);           // [n_entries]
+  float* ring = reinterpret_cast<float*>(smem_raw + a.ring_off);           // [2][KCH][P]
+  const int w = a.w, ww = w * w, P = 8 * ww, NC = 6 * ww;
+  const int b = blockIdx.x / a.G, r = blockIdx.x - b * a.G;
+  const int groups = (a.C + KCH - 1) / KCH;
+  const int n_mine = r < groups ? (groups - r + a.G - 1) / a.G : 0;
+  const int tid = threadIdx.x;
+  pdl_trigger();
+  for (int i = tid; i <= NC; i += kC2eSmallThreads) offs_s[i] = (uint16_t)__ldg(a.offs + i);
+  for (int i = tid; i < a.n_entries; i += kC2eSmallThreads) {
+    pix_s[i] = (uint16_t)__ldg(a.pix + i);
+    wts_s[i] = __ldg(a.wts + i);
+  }
+  auto issue = [&](int i) {                                                 // thread 0: the CTA's i-th group
+    const int c0 = (r + i * a.G) * KCH, kl = min(KCH, a.C - c0);
+    const uint32_t bytes = (uint32_t)(kl * P) * 4u;
+    tma::mbar_expect_tx(&full[i & 1], bytes);
+    tma::bulk_load(ring + (size_t)(i & 1) * KCH * P, a.gequi + ((int64_t)b * a.C + c0) * P, bytes, &full[i & 1]);
+  };
+  if (tid == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0)
+    for (int i = 0; i < min(2, n_mine); ++i) issue(i);
+  for (int i = 0; i < n_mine; ++i) {
+    tma::mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
+    const int c0 = (r + i * a.G) * KCH, kl = min(KCH, a.C - c0);
+    const float* gs = ring + (size_t)(i & 1) * KCH * P;
+    for (int cell = tid; cell < NC; cell += kC2eSmallThreads) {
+      float acc[KCH];
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) acc[c] = 0.0f;
+      const int e0 = offs_s[cell], e1 = offs_s[cell + 1];
+      for (int e = e0; e < e1; ++e) {
+        const float* g = gs + pix_s[e];
+        const float wt = wts_s[e];
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(g[c * P], wt, acc[c]);   // rows beyond kl hold stale finite data; never stored
+      }
+      const int f = cell / ww, rr = cell - f * ww;
+      float* dst = a.gcube + (((int64_t)b * 6 + f) * a.C + c0) * ww + rr;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        if (c < kl) __stcs(dst + (int64_t)c * ww, acc[c]);
+    }
+    __syncthreads();                                     // every thread is done with ring[i & 1]
+    if (tid == 0 && i + 2 < n_mine) issue(i + 2);
+  }
+}
+
+template <int KCH>
 __global__ void __launch_bounds__(kC2eSmallThreads)
 c2e_bwd_gather_kernel(const float* __restrict__ gequi, const int32_t* __restrict__ offs, const int32_t* __restrict__ pix,
                       const float* __restrict__ wts, float* __restrict__ gcube, int C, int w, int groups) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  const float* gs = reinterpret_cast<const float*>(smem_raw + 128);       // [KCH][P] (SMALL)
   const int ww = w * w, P = 8 * ww, NC = 6 * ww;
   const int b = blockIdx.x / groups, c0 = (blockIdx.x - b * groups) * KCH;
   const int kl = min(KCH, C - c0);
   const float* src = gequi + ((int64_t)b * C + c0) * P;
-  if (SMALL) {
-    if (threadIdx.x == 0) {
-      tma::mbar_init(bar, 1);
-      tma::fence_mbar_init();
-      const uint32_t bytes = (uint32_t)(kl * P) * 4u;
-      tma::mbar_expect_tx(bar, bytes);
-      tma::bulk_load(const_cast<float*>(gs), src, bytes, bar);
-    }
-    __syncthreads();
-    tma::mbar_wait(bar, 0);
-    src = gs;
-  }
   for (int cell = threadIdx.x; cell < NC; cell += kC2eSmallThreads) {
     float acc[KCH];
 #pragma unroll
@@ -557,7 +464,7 @@ c2e_bwd_gather_kernel(const float* __restrict__ gequi, const int32_t* __restrict
       const float wt = __ldg(wts + e);
 #pragma unroll
       for (int c = 0; c < KCH; ++c)
-        if (c < kl) acc[c] = fmaf(SMALL ? src[c * P + p] : __ldg(src + (int64_t)c * P + p), wt, acc[c]);
+        if (c < kl) acc[c] = fmaf(__ldg(src + (int64_t)c * P + p), wt, acc[c]);
     }
     const int f = cell / ww, r = cell - f * ww;
     float* dst = gcube + (((int64_t)b * 6 + f) * C + c0) * ww + r;
@@ -702,96 +609,6 @@ c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restric
   }
 }
 
-// w <= 8 (the reference's 7x7 / 8x8 score maps): lane = channel, warp = output pixel. With lanes on pixels
-// (kernel above) the 32 lanes of a load all hit the same 49- / 64-word channel plane and collide in its banks
-// (~3 wavefronts per load, measured: the kernel sat on shared-memory bandwidth at 0.7 TB/s); with lanes on
-// channels and an ODD plane stride every load is conflict-free, the 16 window weights of a pixel are warp-uniform
-// (a per-CTA table, read as broadcasts), and the interior / border summation orders of OpenCV become a
-// warp-uniform branch. Block = (frame, 32 channels): planes come in through coalesced loads into the padded
-// layout, results leave through a [32][tile] staging tile so that global stores stay coalesced.
-constexpr int kCubicLaneThreads = 512;
-constexpr int kCubicTilePix = 256;
-
-__global__ void __launch_bounds__(kCubicLaneThreads)
-c2e_cubic_lanech_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
-                        float* __restrict__ out, int C, int w, int groups) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int ww = w * w, P = 8 * ww;
-  const int S = ww | 1;                                       // odd channel-plane stride: conflict-free across lanes
-  float* in_s = reinterpret_cast<float*>(smem_raw);           // [6][32][S]
-  float4* wt_s = reinterpret_cast<float4*>(in_s + ((6 * 32 * S + 3) & ~3));    // [P][4] : 16 weights per pixel
-  float* out_s = reinterpret_cast<float*>(wt_s + (size_t)P * 4);               // [32][kCubicTilePix + 1]
-  const int b = blockIdx.x / groups, c0 = (blockIdx.x - b * groups) * 32;
-  const int kl = min(32, C - c0);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  pdl_trigger();
-  // weight table (independent of the data): thread = pixel
-  for (int pix = tid; pix < P; pix += kCubicLaneThreads) {
-    const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
-    float cx[4], cy[4];
-    cubic_coeffs(t.fx, cx);
-    cubic_coeffs(t.fy, cy);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      wt_s[pix * 4 + i] = make_float4(__fmul_rn(cy[i], cx[0]), __fmul_rn(cy[i], cx[1]), __fmul_rn(cy[i], cx[2]),
-                                      __fmul_rn(cy[i], cx[3]));
-  }
-  pdl_wait();
-  // planes: coalesced global loads, one channel plane after the other, into the padded layout
-  for (int f = 0; f < 6; ++f) {
-    const float* src = cube + (((int64_t)b * 6 + f) * C + c0) * ww;
-    for (int e = tid; e < kl * ww; e += kCubicLaneThreads) {
-      const int c = e / ww, r = e - c * ww;
-      in_s[(f * 32 + c) * S + r] = __ldg(src + e);
-    }
-  }
-  __syncthreads();
-  const int lim = max(w - 3, 0);
-  const float* lane_in = in_s + lane * S;
-  for (int p0 = 0; p0 < P; p0 += kCubicTilePix) {
-    const int np = min(kCubicTilePix, P - p0);
-    for (int q = warp; q < np; q += kCubicLaneThreads / 32) {
-      const int pix = p0 + q;
-      const CubicTap t = decode_cubic_tap(__ldg(taps + pix));           // warp-uniform
-      const float* src = lane_in + t.face * 32 * S;
-      float wt[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = wt_s[pix * 4 + i];
-        wt[i * 4] = v.x; wt[i * 4 + 1] = v.y; wt[i * 4 + 2] = v.z; wt[i * 4 + 3] = v.w;
-      }
-      float sum = 0.0f;
-      if ((unsigned)t.x0 < (unsigned)lim && (unsigned)t.y0 < (unsigned)lim) {   // window inside the face: row sums
-        const float* r0 = src + t.y0 * w + t.x0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float* r = r0 + i * w;
-          float rs = __fadd_rn(__fmul_rn(r[0], wt[i * 4]), __fmul_rn(r[1], wt[i * 4 + 1]));
-          rs = __fadd_rn(rs, __fmul_rn(r[2], wt[i * 4 + 2]));
-          rs = __fadd_rn(rs, __fmul_rn(r[3], wt[i * 4 + 3]));
-          sum = i == 0 ? rs : __fadd_rn(sum, rs);
-        }
-      } else {                                                                 // border: tap by tap, outside taps skipped
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int yy = t.y0 + i, xx = t.x0 + j;
-            if ((unsigned)yy < (unsigned)w && (unsigned)xx < (unsigned)w)
-              sum = __fadd_rn(sum, __fmul_rn(src[yy * w + xx], wt[i * 4 + j]));
-          }
-      }
-      out_s[lane * (kCubicTilePix + 1) + q] = sum;
-    }
-    __syncthreads();
-    for (int e = tid; e < kl * np; e += kCubicLaneThreads) {
-      const int c = e / np, q = e - c * np;
-      __stcs(out + ((int64_t)b * C + c0 + c) * P + p0 + q, out_s[c * (kCubicTilePix + 1) + q]);
-    }
-    __syncthreads();
-  }
-}
-
 // any w: taps read through the read-only path (the cube of one frame is L2-resident)
 __global__ void __launch_bounds__(kC2eThreads)
 c2e_cubic_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
@@ -876,34 +693,6 @@ static bool try_c2e_max_cluster(const float* cube, const uint32_t* taps, const f
   static const bool enabled = [] { const char* v = getenv("CP360_C2E_CLUSTER"); return !(v && *v == '0'); }();
   if (!enabled || w > 16 || B > 0x3fffffff) return false;
   const int ww = w * w, P = 8 * ww;
-  static const bool lanech = [] { const char* v = getenv("CP360_C2E_LANECH"); return !(v && *v == '0'); }();
-  if (w <= 8 && lanech) {                              // lane = channel kernel: any C, any alignment
-    C2eMaxArgs a;
-    a.cube = cube; a.taps = taps; a.wts = reinterpret_cast<const float4*>(wts); a.sal = sal; a.arg = arg;
-    a.C = (int)C; a.w = w; a.K = kLanechK; a.stages = 2;
-    int G = 8;
-    while (G > 1 && (B * G > 4 * (int64_t)sm_count() || (C + G - 1) / G < kLanechK)) G >>= 1;
-    a.Cg = (int)((C + G - 1) / G);
-    const int S = ww | 1;
-    a.stage_floats = 6 * kLanechK * S;
-    a.ring_off = (P * (16 + 4 + 4 + 4) + 127) & ~127;
-    const size_t smem = (size_t)a.ring_off + (size_t)2 * a.stage_floats * 4;
-    void (*kern)(const C2eMaxArgs) = c2e_max_lanech_kernel<MODE>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    cudaError_t e = launch_kernel_cluster(kern, dim3((unsigned)(B * G)), dim3(kC2eSmallThreads), smem, st, (unsigned)G, a);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("c2e cluster launch failed: %s", cudaGetErrorString(e));
-      *rc_out = CP360_ERR_CUDA;
-      return true;
-    }
-    count_launch();
-    *rc_out = CP360_OK;
-    return true;
-  }
   if (((uintptr_t)cube % 16) != 0) return false;
   int q = 1;
   while ((q * ww) % 4) q <<= 1;                       // 16 B granularity of the bulk copies
@@ -1024,18 +813,6 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
   if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = 8 * w * w;
-  static const bool lanech = [] { const char* v = getenv("CP360_CUBIC_LANECH"); return !(v && *v == '0'); }();
-  if (w <= 8 && lanech) {                               // lane = channel kernel (any alignment, any C)
-    const int ww = w * w, S = ww | 1;
-    const int64_t groups = (C + 31) / 32;
-    CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
-    const size_t smem_l = (size_t)((6 * 32 * S + 3) & ~3) * 4 + (size_t)P * 64 + (size_t)32 * (kCubicTilePix + 1) * 4;
-    CP360_CUDA_OK(cudaFuncSetAttribute(c2e_cubic_lanech_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-    launch_kernel(c2e_cubic_lanech_kernel, (unsigned)(B * groups), kCubicLaneThreads, smem_l, st, cube, taps, equi,
-                  (int)C, w, (int)groups);
-    CP360_LAUNCHED();
-    return CP360_OK;
-  }
   size_t smem = 0;
   int k = small_plan(cube, C, w, &smem);
   if (k > 0) {
@@ -1061,9 +838,11 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
   return CP360_OK;
 }
 
-int cp360_c2e_bwd(const float* gequi, const int32_t* offs, const int32_t* pix, const float* bwts, float* gcube,
-                  int64_t B, int64_t C, int w, void* stream) {
+int cp360_c2e_bwd(const float* gequi, const int32_t* offs, const int32_t* pix, const float* bwts, int n_entries,
+                  float* gcube, int64_t B, int64_t C, int w, void* stream) {
   CP360_CHECK_ARG(B >= 0 && C >= 0 && w > 0 && w <= 8191 && C <= 0x7fffffff, CP360_ERR_BAD_ARG, "bad size");
+  CP360_CHECK_ARG(n_entries >= 0 && (int64_t)n_entries <= (int64_t)32 * w * w, CP360_ERR_BAD_ARG,
+                  "n_entries must be offsets[6*w*w] of cp360_c2e_build_bwd_plan (<= 32*w*w)");
   if (B == 0 || C == 0) return CP360_OK;
   CP360_CHECK_ARG(gequi && gcube, CP360_ERR_BAD_ARG, "null pointer");
   CP360_CHECK_ARG(((uintptr_t)gequi % 4) == 0 && ((uintptr_t)gcube % 4) == 0, CP360_ERR_ALIGN, "tensors must be 4 B aligned");
@@ -1072,17 +851,32 @@ int cp360_c2e_bwd(const float* gequi, const int32_t* offs, const int32_t* pix, c
   rc = require_device();
   if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int P = 8 * w * w;
-  // channel group: 16 (8 at w = 16) gradient planes staged in shared memory for small faces, 8 read in place otherwise
-  const bool small = w <= 16 && ((uintptr_t)gequi % 16) == 0 && (P % 4) == 0;
-  const int kch = (small && w <= 8) ? 16 : 8;
+  const int P = 8 * w * w, NC = 6 * w * w;
+  const bool small = w <= 16 && ((uintptr_t)gequi % 16) == 0 && n_entries <= 65535;   // 16-bit ids in shared memory
+  if (small) {
+    C2eBwdArgs a;
+    a.gequi = gequi; a.offs = offs; a.pix = pix; a.wts = bwts; a.gcube = gcube; a.C = (int)C; a.w = w;
+    a.n_entries = n_entries;
+    const int kch = w <= 8 ? 16 : 8;
+    const int64_t groups = (C + kch - 1) / kch;
+    a.G = (int)std::max<int64_t>(1, std::min<int64_t>(groups, (3 * (int64_t)sm_count() + B - 1) / B));
+    a.pix_off = (64 + 2 * (NC + 1) + 15) & ~15;
+    a.wts_off = (a.pix_off + 2 * n_entries + 15) & ~15;
+    a.ring_off = (a.wts_off + 4 * n_entries + 127) & ~127;
+    const size_t smem = (size_t)a.ring_off + (size_t)2 * kch * P * 4;
+    CP360_CHECK_ARG(B * a.G < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
+    if (smem <= 200 * 1024) {
+      void (*kern)(const C2eBwdArgs) = kch == 16 ? c2e_bwd_small_kernel<16> : c2e_bwd_small_kernel<8>;
+      CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      launch_kernel(kern, (unsigned)(B * a.G), kC2eSmallThreads, smem, st, a);
+      CP360_LAUNCHED();
+      return CP360_OK;
+    }
+  }
+  const int kch = 8;
   const int64_t groups = (C + kch - 1) / kch;
   CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
-  const size_t smem = small ? 128 + (size_t)kch * P * 4 : 0;
-  void (*kern)(const float*, const int32_t*, const int32_t*, const float*, float*, int, int, int) =
-      small ? (kch == 16 ? c2e_bwd_gather_kernel<16, true> : c2e_bwd_gather_kernel<8, true>) : c2e_bwd_gather_kernel<8, false>;
-  if (small) CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(B * groups), kC2eSmallThreads, smem, st>>>(gequi, offs, pix, bwts, gcube, (int)C, w, (int)groups);
+  c2e_bwd_gather_kernel<8><<<(unsigned)(B * groups), kC2eSmallThreads, 0, st>>>(gequi, offs, pix, bwts, gcube, (int)C, w, (int)groups);
   CP360_LAUNCHED();
   return CP360_OK;
 }

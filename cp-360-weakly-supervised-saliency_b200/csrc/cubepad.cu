@@ -612,6 +612,7 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
                           CubeBwdArgs* a, size_t* smem_out) {
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
   if (HoWo > 8191 || n_faces <= 0 || ((uintptr_t)gy % 16) != 0 || ((uintptr_t)gx % 4) != 0) return false;
+  if ((int64_t)6 * C * HW >= 0x7fffffff) return false;         // 32-bit destination offsets inside a cube
   int kq = 1;
   while (kq <= 4 && (kq * HoWo) % 4) kq <<= 1;                 // 16 B granularity of the bulk copies
   if (kq > 4 || C % kq) return false;
@@ -633,6 +634,7 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
   a->n_chunks = (n_faces / 6) * a->cblocks;
   a->work = nullptr;
   a->stage_words = 6 * kmax * HoWo;
+  if (a->stage_words > 65535) return false;                    // 16-bit staged-word field of the position records
   a->offs_off = 3 * kCubeMaxStages * 8;
   a->ent_off = (a->offs_off + (6 * HW + 1) * 2 + 15) & ~15;
   a->pos_off = (a->ent_off + 6 * HoWo * 4 + 15) & ~15;

@@ -146,9 +146,27 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
   constexpr int NJc = NJ > 0 ? NJ : 1;
   const bool tail_ok = FULL || (NJc - 1) * 32 + lane < W;
   if (NJc >= 4) {
-    // wide rows: one row per step, NJ loads in flight
+    // wide rows: one row per step, NJ loads in flight — two rows per step when an epilogue sits between the
+    // load and the store (its dependent ALU chain needs more independent work to hide behind)
+    int r = 0;
+    if (EPI && NJc <= 4) {
 #pragma unroll 1
-    for (int r = 0; r < nr; ++r, sp += W, dp += Wo) {
+      for (; r + 2 <= nr; r += 2, sp += 2 * W, dp += 2 * Wo) {
+        uint32_t v[2][NJc];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int j = 0; j < NJc; ++j)
+            if (j < NJc - 1 || tail_ok) v[k][j] = sp[k * W + j * 32];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int j = 0; j < NJc; ++j)
+            if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + k * Wo + j * 32, epi_apply<EPI>(v[k][j], ep));
+      }
+    }
+#pragma unroll 1
+    for (; r < nr; ++r, sp += W, dp += Wo) {
       uint32_t v[NJc];
 #pragma unroll
       for (int j = 0; j < NJc; ++j)

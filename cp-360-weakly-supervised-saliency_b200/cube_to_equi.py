@@ -9,6 +9,8 @@ The unmodified reference calls F.grid_sample without ``align_corners``; under th
 torch (2.11) that means align_corners=False, which is therefore the default here. Pass
 ``align_corners=True`` for the torch<=1.2 behaviour the reference was written against.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -52,6 +54,7 @@ class Cube2Equi:
             lib = _lib.lib()
             _lib.check(lib.cp360_c2e_build_bwd_plan(w, int(self.align_corners), offs.ctypes.data, None, None))
             n = int(offs[-1])
+            self._bwd_entries = n
             pix, wts = np.empty(max(n, 1), dtype=np.int32), np.empty(max(n, 1), dtype=np.float32)
             _lib.check(lib.cp360_c2e_build_bwd_plan(w, int(self.align_corners), offs.ctypes.data, pix.ctypes.data, wts.ctypes.data))
             p = tuple(torch.from_numpy(a).to(device) for a in (offs, pix, wts))
@@ -100,8 +103,8 @@ class Cube2Equi:
         offs, pix, wts = self._bwd_plan_on(g.device)
         with torch.cuda.device(g.device):
             st = torch.cuda.current_stream().cuda_stream
-            _lib.check(_lib.lib().cp360_c2e_bwd(g.data_ptr(), offs.data_ptr(), pix.data_ptr(), wts.data_ptr(), gx.data_ptr(),
-                                                b, c, w, st))
+            _lib.check(_lib.lib().cp360_c2e_bwd(g.data_ptr(), offs.data_ptr(), pix.data_ptr(), wts.data_ptr(), self._bwd_entries,
+                                                gx.data_ptr(), b, c, w, st))
         return gx
 
     def to_equi_max(self, input_data, out=None):
@@ -124,7 +127,13 @@ class Cube2Equi:
         b, c, w = x.shape[0] // 6, x.shape[1], self.input_w
         sal = torch.empty((b, 2 * w, 4 * w), dtype=torch.float32, device=x.device)
         arg = torch.empty((b, 2 * w, 4 * w), dtype=torch.int32, device=x.device)
-        scratch = torch.empty((b, 2 * w, 4 * w), dtype=torch.int64, device=x.device) if w > 16 else None
+        # the cluster kernel (w <= 16, 16 B-aligned input, channel count a multiple of the bulk-copy quantum) needs no
+        # scratch; the atomic-key path every other case takes does
+        q = 1
+        while (q * w * w) % 4:
+            q <<= 1
+        clustered = w <= 16 and x.data_ptr() % 16 == 0 and c % q == 0 and os.environ.get("CP360_C2E_CLUSTER", "1") != "0"
+        scratch = None if clustered else torch.empty((b, 2 * w, 4 * w), dtype=torch.int64, device=x.device)
         taps, wts = self._plan_on(x.device)
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream

@@ -260,9 +260,11 @@ CP360_API int cp360_c2e_cubic_fwd(const float* cube_dev, const uint32_t* tap_dev
 /* Device, fp32: gcube[6B,C,w,w] = d(c2e)^T(gequi[B,C,2w,4w]) — the gradient of cp360_c2e_fwd
  * (train_temporal.py:167-170 back-propagates through to_equi_nn). A gather over the transposed plan
  * (cp360_c2e_build_bwd_plan, device copies): every cube pixel sums its contributors in a fixed order, no
- * atomics — bit-reproducible, and gcube needs no zero fill. */
+ * atomics — bit-reproducible, and gcube needs no zero fill. n_entries = offsets_host[6*w*w], the length of
+ * pix_dev / bwts_dev (the launch sizes its shared-memory copy of the plan by it). */
 CP360_API int cp360_c2e_bwd(const float* gequi_dev, const int32_t* offsets_dev, const int32_t* pix_dev,
-                  const float* bwts_dev, float* gcube_dev, int64_t B, int64_t C, int w, void* stream);
+                  const float* bwts_dev, int n_entries, float* gcube_dev, int64_t B, int64_t C, int w,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * .npy files either side of the path: cube score files `cube_feat/%06d.npy` [6,1000,7,7]
