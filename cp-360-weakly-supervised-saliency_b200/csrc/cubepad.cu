@@ -619,7 +619,7 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
   // measured on [96,256,32,32]: 48 KB x 3 stages (1 channel per stage) 162 us, 96 KB x 2 (2 channels) 115 us;
   // on the 7x7 / 8x8 / 16x16 sites 64 KB x 3 is the fastest of the settings tried (profiles/README.md)
   const bool deep = g.H > 16;
-  const int stage_kb = std::max(1, env_int("CP360_BWD_STAGE_KB", deep ? 96 : 64));
+  const int stage_kb = std::max(1, env_int("CP360_BWD_STAGE_KB", deep ? 64 : 64));
   int kmax = (stage_kb * 1024) / (6 * HoWo * 4);
   kmax = std::min(kmax, C);
   kmax -= kmax % kq;
@@ -629,16 +629,35 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
     while (p2 * 2 <= kmax) p2 *= 2;
     if (p2 % kq == 0) kmax = p2;
   }
-  int stages = std::min(kCubeMaxStages, std::max(2, env_int("CP360_BWD_STAGES", deep ? 2 : 3)));
+  int stages = std::min(kCubeMaxStages, std::max(2, env_int("CP360_BWD_STAGES", 3)));
   a->C = C; a->kmax = kmax; a->cblocks = (C + kmax - 1) / kmax;
   a->n_chunks = (n_faces / 6) * a->cblocks;
   a->work = nullptr;
   a->stage_words = 6 * kmax * HoWo;
   if (a->stage_words > 65535) return false;                    // 16-bit staged-word field of the position records
-  a->offs_off = 3 * kCubeMaxStages * 8;
-  a->ent_off = (a->offs_off + (6 * HW + 1) * 2 + 15) & ~15;
-  a->pos_off = (a->ent_off + 6 * HoWo * 4 + 15) & ~15;
-  a->ring_off = (a->pos_off + 6 * HW * 8 + 127) & ~127;
+  // position words hold a 12-bit list start and a 4-bit copy count: check both against this geometry
+  {
+    const int n_halo_total = 6 * (HoWo - HW);
+    if (n_halo_total >= 4096) return false;
+    const int pm = std::max(std::max(g.pl, g.pr), std::max(g.pt, g.pd));
+    int max_cnt = 0;
+    for (int f = 0; f < 6; ++f)                                // only corner neighbourhoods can collect many copies
+      for (int y : {0, g.H - 1})
+        for (int x : {0, g.W - 1}) {
+          for (int dy = 0; dy < std::min(pm, g.H); ++dy)
+            for (int dx = 0; dx < std::min(pm, g.W); ++dx) {
+              const int yy = y == 0 ? dy : g.H - 1 - dy, xx = x == 0 ? dx : g.W - 1 - dx;
+              int cnt = 0;
+              cubepad_for_each_copy(g, f, yy, xx, [&](int, int, int) { ++cnt; });
+              max_cnt = std::max(max_cnt, cnt);
+            }
+        }
+    if (max_cnt > 15) return false;
+  }
+  a->lut_off = 3 * kCubeMaxStages * 8;
+  a->ent_off = (a->lut_off + 6 * HW * 4 + 15) & ~15;
+  a->ring_off = (a->ent_off + 6 * (HoWo - HW) * 2 + 127) & ~127;
+  a->d_HW = make_fastdiv((uint32_t)HW);
   size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
   while (smem > 220 * 1024 && stages > 2) {
     --stages;

@@ -8,12 +8,14 @@
 // PADDED gradient is what is staged: six TMA bulk loads (one contiguous k*Ho*Wo chunk per face) per
 // tile, `stages` tiles ahead, every gy element read from DRAM exactly once, no atomics.
 //
-// A CSR table in shared memory, built once per CTA from cubepad_geom.h (cubepad_for_each_copy: the
-// push table inverted), lists for each input position (face, y, x) the staged words that hold its
-// copies: the interior copy first, then the halo copies in the fixed (entry, u, v) order — the same
-// order as cubepad_bwd_band_kernel, so both paths produce bit-identical, reproducible sums. A consumer
-// thread owns fixed input positions and walks the channels: LDS (+ adds for edge pixels) -> STG,
-// consecutive lanes on consecutive words of the gx plane.
+// Tables in shared memory, built once per CTA from cubepad_geom.h (cubepad_for_each_copy: the push table
+// inverted): one word per input position (face, y, x) — the staged word of its interior copy, the number of halo
+// positions that copied it and where their list starts — and a short list of 16-bit staged words for the halo
+// copies (only the pixels within a pad width of a face edge have any: 12 % at H = 32). Halo copies are summed in
+// the fixed (entry, u, v) order — the same order as cubepad_bwd_band_kernel, so both paths produce bit-identical,
+// reproducible sums. A consumer thread owns fixed input positions and walks the channels: LDS (+ adds for edge
+// pixels) -> STG, consecutive lanes on consecutive words of the gx plane. (Round 1 kept 14 B of tables per position
+// — 89 KB at H = 32 — which left room for only two 55 KB stages; at 4 B per position a third stage fits.)
 #pragma once
 #include "common.cuh"
 #include "cubepad_cube.cuh"
@@ -32,10 +34,10 @@ struct CubeBwdArgs {
   int32_t cblocks;
   int32_t stages;
   int32_t stage_words;  // 6 * kmax * Ho * Wo
-  int32_t offs_off;     // byte offset of the CSR row offsets (uint16 [6*H*W + 1])
-  int32_t ent_off;      // byte offset of the CSR entries (uint32 [6*Ho*Wo], staged word of channel 0)
-  int32_t pos_off;      // byte offset of the per-position records (uint2 [6*H*W])
+  int32_t lut_off;      // byte offset of the position table (uint32 [6*H*W]): word:16 | halo copies:4 | list start:12
+  int32_t ent_off;      // byte offset of the halo lists (uint16 [6*(Ho*Wo - H*W)], staged word of channel 0)
   int32_t ring_off;     // byte offset of the staging ring
+  FastDiv d_HW;         // e / (H*W)
 };
 
 // TK > 0: kmax known at compile time (the channel walk of a full chunk is unrolled in batches of 8)
@@ -46,10 +48,8 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [stages]
   uint64_t* empty = full + kCubeMaxStages;                                // [stages]
   int64_t* chunk_of = reinterpret_cast<int64_t*>(empty + kCubeMaxStages); // [stages] chunk id staged there, -1: end
-  uint16_t* offs = reinterpret_cast<uint16_t*>(smem_raw + a.offs_off);
-  uint32_t* ent = reinterpret_cast<uint32_t*>(smem_raw + a.ent_off);
-  // per input position: .x = staged word of its interior copy, .y = face << 29 | halo copies << 16 | pixel
-  uint2* pos = reinterpret_cast<uint2*>(smem_raw + a.pos_off);
+  uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + a.lut_off);
+  uint16_t* ent = reinterpret_cast<uint16_t*>(smem_raw + a.ent_off);
   const float* ring = reinterpret_cast<const float*>(smem_raw + a.ring_off);
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
   const int n_in = 6 * HW;
@@ -75,23 +75,22 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     }
     tma::fence_mbar_init();
   }
-  // ---- CSR of the transposed map. Pass 1: copies per input position (interior copy included)
+  // ---- tables. Pass 1: halo copies per input position (only pixels within a pad width of a face edge have any:
+  // skip the plate walk elsewhere — at H = 32 that is 88 % of the positions)
   for (int e = tid; e < n_in; e += blockDim.x) {
     const int f = e / HW, r = e - f * HW;
     const int y = r / g.W, x = r - y * g.W;
-    int cnt = 1;
-    // only pixels within a pad width of a face edge are ever copied into a halo: skip the plate walk elsewhere
-    // (at H = 32 that is 88 % of the positions, and this prologue was a third of the kernel's instructions)
+    int cnt = 0;
     if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) < pm)
       cubepad_for_each_copy(g, f, y, x, [&](int, int, int) { ++cnt; });
-    offs[e + 1] = (uint16_t)cnt;
+    lut[e] = (uint32_t)cnt;
   }
   __syncthreads();
-  if (warp == 0) {                                     // exclusive scan, one contiguous segment per lane
+  if (warp == 0) {                                     // exclusive scan in place, one contiguous segment per lane
     const int seg = (n_in + 31) / 32;
     const int b = min(lane * seg, n_in), e1 = min(b + seg, n_in);
     int sum = 0;
-    for (int i = b; i < e1; ++i) sum += offs[i + 1];
+    for (int i = b; i < e1; ++i) sum += (int)lut[i];
     int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -100,27 +99,26 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     }
     int run = incl - sum;
     for (int i = b; i < e1; ++i) {
-      const int c = offs[i + 1];
+      const int c = (int)lut[i];
+      lut[i] = (uint32_t)run | (uint32_t)c << 16;      // start | count (start < 4096, count < 16: checked on the host)
       run += c;
-      offs[i + 1] = (uint16_t)run;                     // total = 6*Ho*Wo <= 49146 fits
     }
-    if (lane == 0) offs[0] = 0;
   }
   __syncthreads();
-  // Pass 2: the entries — staged word (channel 0 of the chunk) of every copy
+  // Pass 2: the halo lists and the final position words
   for (int e = tid; e < n_in; e += blockDim.x) {
     const int f = e / HW, r = e - f * HW;
     const int y = r / g.W, x = r - y * g.W;
-    const int o0 = offs[e];
-    int o = o0;
-    const uint32_t inner = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
-    ent[o++] = inner;
-    if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) < pm)
+    const uint32_t sc = lut[e];
+    const int start = (int)(sc & 0xffffu), cnt = (int)(sc >> 16);
+    if (cnt) {
+      int o = start;
       cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
-        ent[o++] = (uint32_t)(dface * fstride + oy * g.Wo + ox);
+        ent[o++] = (uint16_t)(dface * fstride + oy * g.Wo + ox);
       });
-    // .x = staged word of the interior copy | halo copies << 16; .y = destination word inside the chunk's output
-    pos[e] = make_uint2(inner | (uint32_t)(o - o0 - 1) << 16, (uint32_t)(f * a.C * HW + r));
+    }
+    const uint32_t inner = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
+    lut[e] = inner | (uint32_t)cnt << 16 | (uint32_t)start << 20;
   }
   __syncthreads();
   pdl_wait();
@@ -169,6 +167,7 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
 
   // ---------------- consumers
   const int ctid = tid - 32;
+  const int64_t CHW = (int64_t)a.C * HW;
   int s = 0;
   uint32_t ph = 0;
   while (true) {
@@ -184,18 +183,18 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
       constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
 #pragma unroll 1
       for (int e = ctid; e < n_in; e += n_cons) {
-        const uint2 pe = pos[e];
-        const int n_halo = (int)(pe.x >> 16);
-        float* __restrict__ dp = out + pe.y;
-        const float* sp0 = in_s + (pe.x & 0xffffu);
-        const int o0 = n_halo ? (int)offs[e] : 0;
+        const uint32_t l = lut[e];
+        const int n_halo = (int)((l >> 16) & 15u), o0 = (int)(l >> 20);
+        const int f = fdiv(e, a.d_HW);
+        float* __restrict__ dp = out + (int64_t)f * CHW + (e - f * HW);
+        const float* sp0 = in_s + (l & 0xffffu);
 #pragma unroll
         for (int c8 = 0; c8 < TK; c8 += KB) {
           float acc[KB];
 #pragma unroll
           for (int j = 0; j < KB; ++j) acc[j] = sp0[(c8 + j) * HoWo];
 #pragma unroll 1
-          for (int o = o0 + 1; o <= o0 + n_halo; ++o) {
+          for (int o = o0; o < o0 + n_halo; ++o) {
             const float* sp = in_s + ent[o] + c8 * HoWo;
 #pragma unroll
             for (int j = 0; j < KB; ++j) acc[j] += sp[j * HoWo];
@@ -207,15 +206,15 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     } else {
 #pragma unroll 1
       for (int e = ctid; e < n_in; e += n_cons) {
-        const uint2 pe = pos[e];
-        const int n_halo = (int)(pe.x >> 16);
-        float* __restrict__ dp = out + pe.y;
-        const int o0 = n_halo ? (int)offs[e] : 0;
-        const int inner = (int)(pe.x & 0xffffu);
+        const uint32_t l = lut[e];
+        const int n_halo = (int)((l >> 16) & 15u), o0 = (int)(l >> 20);
+        const int f = fdiv(e, a.d_HW);
+        float* __restrict__ dp = out + (int64_t)f * CHW + (e - f * HW);
+        const int inner = (int)(l & 0xffffu);
 #pragma unroll 1
         for (int cc = 0; cc < kl; ++cc) {
           float acc = in_s[inner + cc * HoWo];
-          for (int o = o0 + 1; o <= o0 + n_halo; ++o) acc += in_s[ent[o] + cc * HoWo];
+          for (int o = o0; o < o0 + n_halo; ++o) acc += in_s[ent[o] + cc * HoWo];
           __stcs(dp + cc * HW, acc);
         }
       }

@@ -372,7 +372,9 @@ class SphericalPipeline:
 
     def h2d_probe(self, host_batches, repeats=1):
         """Upload-only ceiling of process_host: the same pinned batches through the same staging ring and copy
-        streams, no kernels, no D2H. Returns GB/s (CUDA events on the compute stream)."""
+        streams, no kernels, no D2H. Returns (GB/s, seconds, bytes) — CUDA events on the compute stream; with several
+        ranks on one host the aggregate is all ranks' bytes over the SLOWEST rank's seconds (ranks that finish early
+        hand their share of the uplink to the others, so per-rank rates must not be summed)."""
         dev = self.device
         if getattr(self, "_stage", None) is None:
             raise RuntimeError("call process_host once first (it owns the staging ring)")
@@ -395,7 +397,8 @@ class SphericalPipeline:
             compute.wait_stream(cs)
         e1.record(compute)
         compute.synchronize()
-        return nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        sec = e0.elapsed_time(e1) * 1e-3
+        return nbytes / sec / 1e9, sec, nbytes
 
 class TemporalCubePadSequence:
     """The hot-path work of the ConvLSTM temporal model (BASELINE.json configs[3]) for B
