@@ -25,6 +25,7 @@ SIGNATURES = {
     "cp360_cubepad_pick_algo": (c_i32, [c_i64, c_i64] + [c_i32] * 8),
     "cp360_cubepad_fused_fwd": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 6 + [c_vp, c_vp, c_i32, c_i64, c_i64, c_vp]),
     "cp360_cubepad_autotune": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 7 + [c_vp]),
+    "cp360_cubepad_set_tiling": (c_i32, [c_i64, c_i64] + [c_i32] * 14),
     "cp360_cubepad_tune_info": (c_i32, [c_i64, c_i64] + [c_i32] * 6 + [ctypes.c_char_p, c_i32]),
     "cp360_cubepad_build_inverse_map": (c_i32, [c_i32] * 6 + [c_vp, c_vp]),
     "cp360_cubepad_bwd_f32": (c_i32, [c_vp, c_vp, c_i64, c_i64] + [c_i32] * 6 + [c_vp]),

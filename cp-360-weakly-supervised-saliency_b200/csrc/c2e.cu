@@ -609,6 +609,90 @@ c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restric
   }
 }
 
+// 8 < w <= 16, channel-interleaved staging: the kernel above reads one float per (tap, channel) and its 32 lanes
+// collide in the banks of a single 49..256-word channel plane — 16 taps x ~2 wavefronts per pixel·channel, which is
+// what bounds it (shared-memory bandwidth; ncu: 0.9-1.4 TB/s of DRAM-side bytes). Here the planes of a group of KS
+// channels are TRANSPOSED on the way into shared memory ([face][pixel][KS + 4] floats: coalesced global loads,
+// scattered 4-byte stores — 5 % of the kernel's shared-memory traffic), so a tap of four channels is ONE 16-byte
+// load and lanes on different pixels fall into different bank groups (pixel stride = KS + 4 floats = odd multiple
+// of 16 B): half the wavefronts per output value and a quarter of the load instructions. Same arithmetic, bit-exact.
+constexpr int kCubicTThreads = 256;
+
+template <int KS>
+__global__ void __launch_bounds__(kCubicTThreads)
+c2e_cubic_t_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
+                   float* __restrict__ out, int C, int w, int groups) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int PS = KS + 4;                                  // pixel stride in floats
+  float* in_t = reinterpret_cast<float*>(smem_raw);           // [6][ww][PS]
+  const int ww = w * w, P = 8 * ww;
+  const int b = blockIdx.x / groups, c0 = (blockIdx.x - b * groups) * KS;
+  const int kl = min(KS, C - c0);
+  const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  const float inv_ww = 1.0f / (float)ww;
+  for (int f = 0; f < 6; ++f) {
+    const float* src = cube + (((int64_t)b * 6 + f) * C + c0) * ww;
+    float* dst = in_t + (size_t)f * ww * PS;
+    for (int e = tid; e < kl * ww; e += kCubicTThreads) {
+      const int c = (int)(((float)e + 0.5f) * inv_ww);        // e / ww (exact for these sizes)
+      dst[(e - c * ww) * PS + c] = __ldg(src + e);
+    }
+  }
+  __syncthreads();
+  const int nq = (kl + 3) >> 2;
+  const int lim = max(w - 3, 0);
+  for (int pix = tid; pix < P; pix += kCubicTThreads) {
+    const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
+    float cx[4], cy[4];
+    cubic_coeffs(t.fx, cx);
+    cubic_coeffs(t.fy, cy);
+    const bool inside = (unsigned)t.x0 < (unsigned)lim && (unsigned)t.y0 < (unsigned)lim;
+    unsigned ok = 0;
+    int off[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yy = t.y0 + i, xx = t.x0 + j;
+        const bool v = (unsigned)yy < (unsigned)w && (unsigned)xx < (unsigned)w;
+        ok |= (unsigned)v << (i * 4 + j);
+        off[i * 4 + j] = v ? (yy * w + xx) * PS : 0;
+      }
+    const float* base = in_t + (size_t)t.face * ww * PS;
+    float* dst = out + ((int64_t)b * C + c0) * P + pix;
+    for (int q = 0; q < nq; ++q) {
+      float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (inside || (ok & (1u << (i * 4 + j)))) {
+            const float4 v = *reinterpret_cast<const float4*>(base + off[i * 4 + j] + 4 * q);
+            const float wt = __fmul_rn(cy[i], cx[j]);
+            const float s4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float pr = __fmul_rn(s4[k], wt);
+              if (inside) rs[k] = j == 0 ? pr : __fadd_rn(rs[k], pr);      // row sum ((S0*w0 + S1*w1) + S2*w2) + S3*w3
+              else sum[k] = __fadd_rn(sum[k], pr);                         // border: tap by tap, outside taps skipped
+            }
+          }
+        }
+        if (inside) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sum[k] = i == 0 ? rs[k] : __fadd_rn(sum[k], rs[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (4 * q + k < kl) __stcs(dst + (int64_t)(4 * q + k) * P, sum[k]);
+    }
+  }
+}
+
 // any w: taps read through the read-only path (the cube of one frame is L2-resident)
 __global__ void __launch_bounds__(kC2eThreads)
 c2e_cubic_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
@@ -813,6 +897,22 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
   if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = 8 * w * w;
+  static const bool transposed = [] { const char* v = getenv("CP360_CUBIC_T"); return !(v && *v == '0'); }();
+  // channel-interleaved staging (any C, any alignment). Measured on B200 at B = 32: [192,256,16,16] 111 us vs 129 us for
+  // the plane-major kernel, but 104 vs 95 us at [192,1000,8,8] — so it is the default only above w = 8
+  // (CP360_CUBIC_T=2 forces it for every w <= 16, =0 disables it)
+  static const bool transposed_all = [] { const char* v = getenv("CP360_CUBIC_T"); return v && *v == '2'; }();
+  if (w <= 16 && transposed && (w > 8 || transposed_all)) {
+    const int ks = w <= 8 ? 32 : 8;
+    const int64_t groups = (C + ks - 1) / ks;
+    CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
+    const size_t smem_t = (size_t)6 * w * w * (ks + 4) * 4;
+    void (*kern)(const float*, const uint32_t*, float*, int, int, int) = ks == 32 ? c2e_cubic_t_kernel<32> : c2e_cubic_t_kernel<8>;
+    CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    launch_kernel(kern, (unsigned)(B * groups), kCubicTThreads, smem_t, st, cube, taps, equi, (int)C, w, (int)groups);
+    CP360_LAUNCHED();
+    return CP360_OK;
+  }
   size_t smem = 0;
   int k = small_plan(cube, C, w, &smem);
   if (k > 0) {

@@ -585,7 +585,9 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   CP360_CUBE_CASE(28, 1) CP360_CUBE_CASE(28, 2) CP360_CUBE_CASE(28, 4)
   CP360_CUBE_CASE(16, 4) CP360_CUBE_CASE(16, 8) CP360_CUBE_CASE(16, 16)
   CP360_CUBE_CASE(14, 4) CP360_CUBE_CASE(14, 8) CP360_CUBE_CASE(14, 16)
-  CP360_CUBE_CASE(8, 16) CP360_CUBE_CASE(8, 32) CP360_CUBE_CASE(8, 64) CP360_CUBE_CASE(7, 16) CP360_CUBE_CASE(7, 32) CP360_CUBE_CASE(7, 64)
+  CP360_CUBE_CASE(8, 4) CP360_CUBE_CASE(8, 8) CP360_CUBE_CASE(8, 16) CP360_CUBE_CASE(8, 32) CP360_CUBE_CASE(8, 64)
+  CP360_CUBE_CASE(7, 4) CP360_CUBE_CASE(7, 8) CP360_CUBE_CASE(7, 16) CP360_CUBE_CASE(7, 32) CP360_CUBE_CASE(7, 64)
+  CP360_CUBE_CASE(16, 1) CP360_CUBE_CASE(16, 2) CP360_CUBE_CASE(14, 1) CP360_CUBE_CASE(14, 2)
 #undef CP360_CUBE_CASE
 #define CP360_CUBE_K(KK) \
   case KK: kern = epi ? cubepad_cube2_kernel<0, 0, KK, true> : cubepad_cube2_kernel<0, 0, KK, false>; break;
@@ -599,8 +601,10 @@ static int launch_cube2(const void* x, void* y, int64_t n_faces, int C, const Cu
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cons_warps = std::min(kCubeMaxConsWarps, std::max(1, knob("CP360_CUBE_WARPS", t_tune ? t_tune->cube_warps : 0, 16)));
   a.work = acquire_work_counter(st);
-  // every CTA should own at least ~2 chunks
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count() * per_sm));
+  // one CTA per SM, or per chunk when there are fewer chunks than SMs: a small problem (the reference's batch_size 1)
+  // is latency-bound, and spreading it over more SMs shortens its data phase more than a second chunk per CTA
+  // would save in prologues
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(a.n_chunks, (int64_t)sm_count() * per_sm));
   launch_kernel(kern, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);
   CP360_LAUNCHED();
   return CP360_OK;
@@ -960,11 +964,13 @@ static std::vector<TuneCfg> tune_candidates(const CubePadGeom& g, int64_t n_face
         }
     }
   }
+  const bool tiny = n_faces * C * (int64_t)HW * 4 < ((int64_t)32 << 20);   // small stages spread a small problem over more SMs
   if (g.H <= 45)
-    for (int kb : {24, 48, 96})
+    for (int kb : {6, 12, 24, 48, 96})
       for (int stages : {2, 3, 4})
         for (int warps : {8, 16}) {
-          if (kb == 24 && stages == 2) continue;
+          if (kb <= 24 && stages == 2) continue;
+          if (kb < 24 && !tiny) continue;
           TuneCfg c; c.algo = ALGO_CUBE2; c.cube_stage_kb = kb; c.cube_stages = stages; c.cube_warps = warps;
           t_tune = &c;
           const bool ok = cube2_plan(g, n_faces, C, &ca, &smem, &per_sm);
@@ -1103,7 +1109,8 @@ int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, in
   TuneCfg c;
   if (!tuned_lookup(tune_key(g, n_faces, (int)C), &c)) return CP360_OK;
   char src[48];
-  if (c.from_table) snprintf(src, sizeof(src), "table@%d frames", c.from_table);
+  if (c.from_table < 0) snprintf(src, sizeof(src), "set by the caller");
+  else if (c.from_table) snprintf(src, sizeof(src), "table@%d frames", c.from_table);
   else snprintf(src, sizeof(src), "autotuned");
   if (c.algo == ALGO_ROW)
     snprintf(buf, (size_t)buf_len, "row rb=%d tile_kb=%d order=%d slots=%d (%.1f us, %s)", c.row_rb, c.row_tile_kb,
@@ -1138,6 +1145,28 @@ int cp360_cubepad_autotune(const void* x, void* y, int64_t n_faces, int64_t C, i
   return CP360_OK;
 }
 
+int cp360_cubepad_set_tiling(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd, int algo,
+                             int row_rb, int row_order, int row_slots, int row_tile_kb, int cube_stage_kb,
+                             int cube_stages, int cube_warps) {
+  CubePadGeom g;
+  CP360_CHECK_ARG(make_geom(H, W, pl, pr, pt, pd, &g) && C > 0 && C <= 0x7fffffff && n_faces > 0 && n_faces % 6 == 0,
+                  CP360_ERR_SHAPE, "not a CubePad problem");
+  const TuneKey key = tune_key(g, n_faces, (int)C);
+  std::lock_guard<std::mutex> lock(g_tuned_mutex);
+  if (algo == ALGO_AUTO) {                                 // forget: back to the table / heuristics
+    g_tuned.erase(key);
+    return CP360_OK;
+  }
+  CP360_CHECK_ARG(algo == ALGO_ROW || algo == ALGO_CUBE2, CP360_ERR_BAD_ARG, "tilings exist for the row (5) and cube-tile (6) kernels");
+  TuneCfg c;
+  c.algo = algo;
+  c.row_rb = row_rb; c.row_order1 = row_order + 1; c.row_slots = row_slots; c.row_tile_kb = row_tile_kb;
+  c.cube_stage_kb = cube_stage_kb; c.cube_stages = cube_stages; c.cube_warps = cube_warps;
+  c.from_table = -1;
+  g_tuned[key] = c;
+  return CP360_OK;
+}
+
 int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, int H, int W, int pl,
                            int pr, int pt, int pd, int elem_bytes, int algo, void* stream) {
   CubePadGeom g;
@@ -1158,7 +1187,10 @@ int cp360_cubepad_fwd_algo(const void* x, void* y, int64_t n_faces, int64_t C, i
   if (algo == ALGO_AUTO && fast_ok) {
     const TuneKey key = tune_key(g, n_faces, (int)C);
     TuneCfg cfg;
-    if (tuned_lookup(key, &cfg)) return run_cfg(cfg, x, y, n_faces, (int)C, g, st);
+    if (tuned_lookup(key, &cfg)) {
+      rc = run_cfg(cfg, x, y, n_faces, (int)C, g, st);
+      if (rc != CP360_ERR_SHAPE) return rc;                     // a registered tiling that does not apply: heuristics
+    }
     if (!t_fused && autotune_allowed(n_faces, (int)C, g, st) && autotune(x, y, n_faces, (int)C, g, st, &cfg)) {
       std::lock_guard<std::mutex> lock(g_tuned_mutex);
       g_tuned[key] = cfg;

@@ -113,6 +113,15 @@ CP360_API int cp360_cubepad_fused_fwd(const float* x_dev, float* y_dev, int64_t 
 CP360_API int cp360_cubepad_autotune(const void* x_dev, void* y_dev, int64_t n_faces, int64_t C, int H, int W,
                            int pl, int pr, int pt, int pd, int effort, void* stream);
 
+/* Host: register a tiling for one problem on the current device (what cp360_cubepad_autotune does with its winner;
+ * used by tools/tune_chain.py, which times candidates inside a whole chain of kernels instead of in isolation).
+ * algo 5 = row kernel (row_rb rows per band or row_tile_kb KB of whole planes per tile, dealing order 0 / 2, ring
+ * depth), 6 = cube-tile kernel (stage KB, stages, consumer warps); 0 = forget the registration. A tiling that does
+ * not apply to the problem makes the launch fall back to the other kernel's heuristics. No allocation, no sync. */
+CP360_API int cp360_cubepad_set_tiling(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,
+                             int algo, int row_rb, int row_order, int row_slots, int row_tile_kb,
+                             int cube_stage_kb, int cube_stages, int cube_warps);
+
 /* Host: human-readable tiling cp360_cubepad_fwd uses for this problem on the current device and where it
  * came from ("" = shape heuristics: no autotune result and no table row for this site). */
 CP360_API int cp360_cubepad_tune_info(int64_t n_faces, int64_t C, int H, int W, int pl, int pr, int pt, int pd,

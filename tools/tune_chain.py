@@ -1,0 +1,203 @@
+#!/usr/bin/env python
+"""In-chain CubePad tiling search (GPU box) — the second pass behind csrc/cubepad_tuned.h.
+
+tools/tune_table.py times every candidate tiling of a site in ISOLATION (cold, dirty L2). Inside a chain of
+kernels the ranking can differ (band height is a cliff, not a slope: profiles/README.md), so this tool re-ranks
+the candidates of every cubic-ResNet-50 site by the time of the WHOLE chain step (CUDA-graph replay of
+SphericalPipeline.step, the order one network forward touches the sites in) with that one site's tiling swapped
+through cp360_cubepad_set_tiling — coordinate descent, `--passes` sweeps over the sites. The ConvLSTM-side sites are
+searched the same way inside TemporalCubePadSequence.window_batch. Reads the isolated table (the starting point and
+the rows of everything not re-ranked here) and writes the merged header.
+
+    python tools/tune_chain.py --base gpurun_out/x/cubepad_tuned.h --out gpurun_out/x [--frames 1,2,4,8,16,32,64]
+"""
+import argparse
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["CP360_TUNED_TABLE"] = "0"
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import cp360_b200  # noqa: E402
+from cp360_b200 import _lib  # noqa: E402
+
+ROW_RE = re.compile(r"^\s*\{(\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), (\d+), ([\d.]+)f\},")
+
+
+def read_table(path):
+    rows = {}
+    for line in open(path):
+        m = ROW_RE.match(line)
+        if m:
+            v = [int(x) for x in m.groups()[:12]]
+            rows[tuple(v[:4])] = dict(algo=v[4], row_rb=v[5], row_order1=v[6], row_slots=v[7], row_tile_kb=v[8],
+                                      cube_stage_kb=v[9], cube_stages=v[10], cube_warps=v[11], us=float(m.group(13)))
+    return rows
+
+
+def candidates(C, H, p, n_faces=192):
+    """The tuner's candidate set (csrc/cubepad.cu: tune_candidates), restated."""
+    out = []
+    tiny = n_faces * C * H * H * 4 < (32 << 20)
+    W = H
+    if H >= 24:
+        if H * W * 4 > 6144:
+            rbs = []
+
+            def add(rb):
+                if 1 <= rb < H and 2560 <= rb * W * 4 <= 8192 and rb not in rbs:
+                    rbs.append(rb)
+            for n in range(2, H + 1):
+                rb = (H + n - 1) // n
+                add(rb)
+                if W < 128:
+                    add((rb + 3) // 4 * 4)
+            if not rbs:
+                rbs.append(max(1, 4608 // (W * 4)))
+            for rb in rbs:
+                for order in (0, 2):
+                    for slots in (2, 3, 4):
+                        out.append(dict(algo=5, row_rb=rb, row_order1=order + 1, row_slots=slots, row_tile_kb=0,
+                                        cube_stage_kb=0, cube_stages=0, cube_warps=0))
+        else:
+            for kb in (4, 8):
+                for order in (0, 2):
+                    out.append(dict(algo=5, row_rb=0, row_order1=order + 1, row_slots=3, row_tile_kb=kb,
+                                    cube_stage_kb=0, cube_stages=0, cube_warps=0))
+    if H <= 45 and (6 * H * H * 4) <= 96 * 1024:
+        for kb in (6, 12, 24, 48, 96):
+            for stages in (2, 3, 4):
+                for warps in (8, 16):
+                    if kb <= 24 and stages == 2:
+                        continue
+                    if kb < 24 and not tiny:
+                        continue
+                    if kb * 1024 < 6 * H * H * 4 and kb != 24:          # below one channel per stage: same as the next size up
+                        continue
+                    if kb * stages > 200:
+                        continue
+                    out.append(dict(algo=6, row_rb=0, row_order1=0, row_slots=0, row_tile_kb=0, cube_stage_kb=kb,
+                                    cube_stages=stages, cube_warps=warps))
+    return out
+
+
+def set_tiling(lib, n_faces, C, H, p, cfg):
+    if cfg is None:
+        _lib.check(lib.cp360_cubepad_set_tiling(n_faces, C, H, H, p, p, p, p, 0, 0, 0, 0, 0, 0, 0, 0))
+    else:
+        _lib.check(lib.cp360_cubepad_set_tiling(n_faces, C, H, H, p, p, p, p, cfg["algo"], cfg["row_rb"], cfg["row_order1"] - 1,
+                                                cfg["row_slots"], cfg["row_tile_kb"], cfg["cube_stage_kb"], cfg["cube_stages"],
+                                                cfg["cube_warps"]))
+
+
+def time_graph(capture, reps):
+    g = capture()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / reps)
+    del g
+    return best * 1e3                                     # us per step
+
+
+def search(lib, sites, n_faces, start, capture, reps, passes, log, tag):
+    cur = {s: start.get(s) for s in sites}
+    for s, cfg in cur.items():
+        set_tiling(lib, n_faces, s[0], s[1], s[2], cfg)
+    base = time_graph(capture, reps)
+    log.append("%s start %.1f us/step" % (tag, base))
+    best_t = base
+    for ps in range(passes):
+        for s in sites:
+            C, H, p = s
+            win = None
+            for cfg in candidates(C, H, p, n_faces):
+                set_tiling(lib, n_faces, C, H, p, cfg)
+                try:
+                    t = time_graph(capture, reps)
+                except Exception:                        # noqa: BLE001 - a tiling that does not apply
+                    continue
+                if t < best_t * 0.996:                   # keep the incumbent unless clearly beaten (timing noise ~0.3 %)
+                    best_t, win = t, cfg
+            if win is not None:
+                cur[s] = win
+            set_tiling(lib, n_faces, C, H, p, cur[s])
+        log.append("%s pass %d: %.1f us/step (%.2f %% better than start)" % (tag, ps + 1, best_t, 100 * (base - best_t) / base))
+        print(log[-1], flush=True)
+    return cur, best_t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--base", required=True)
+    ap.add_argument("--out", default="gpurun_out/tune")
+    ap.add_argument("--frames", default="1,2,4,8,16,32,64")
+    ap.add_argument("--passes", type=int, default=2)
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    dev = torch.device("cuda", 0)
+    lib = _lib.lib()
+    table = read_table(args.base)
+    log = []
+    for cube in (256, 224):
+        pipe = cp360_b200.SphericalPipeline(960, 1920, cube, 1000, 2048, device=dev)
+        sites = list(dict.fromkeys(pipe.sites))
+        for B in [int(v) for v in args.frames.split(",")]:
+            pipe.allocate(B)
+            frames = pipe.synthetic_frames(B)
+            start = {s: table.get((s[1], s[2], s[0], B)) for s in sites}
+            reps = max(3, min(40, int(4000 / (40 + 40 * B))))
+            cur, t = search(lib, sites, 6 * B, start, lambda: pipe.capture(frames), reps, args.passes, log,
+                            "chain cube %d B %d" % (cube, B))
+            for s, cfg in cur.items():
+                if cfg is not None:
+                    table[(s[1], s[2], s[0], B)] = dict(cfg, us=cfg.get("us", 0.0))
+            for s in sites:
+                set_tiling(lib, 6 * B, s[0], s[1], s[2], None)
+            del frames
+        del pipe
+        torch.cuda.empty_cache()
+    for (c, w) in ((2048, 8), (1000, 7)):
+        for B in [int(v) for v in args.frames.split(",") if int(v) <= 32]:
+            seq = cp360_b200.TemporalCubePadSequence(c, c, w, 5, device=dev, fused_cat=False)
+            seq.allocate(B)
+            sites = list(dict.fromkeys(seq.sites()))
+            start = {s: table.get((s[1], s[2], s[0], B)) for s in sites}
+            cur, t = search(lib, sites, 6 * B, start, seq.capture, 5, 1, log, "clstm %dx%d B %d" % (c, w, B))
+            for s, cfg in cur.items():
+                if cfg is not None:
+                    table[(s[1], s[2], s[0], B)] = dict(cfg, us=cfg.get("us", 0.0))
+            for s in sites:
+                set_tiling(lib, 6 * B, s[0], s[1], s[2], None)
+            del seq
+            torch.cuda.empty_cache()
+    head = open(args.base).read().split("static const TunedRow kTunedTable[] = {")[0]
+    head = head.replace("cold dirty L2 between candidates).", "cold dirty L2 between candidates),\n// then re-ranked inside the whole chain of "
+                        "kernels by tools/tune_chain.py (CUDA-graph replay of the step, one site's tiling swapped at a time).")
+    with open(os.path.join(args.out, "cubepad_tuned.h"), "w") as f:
+        f.write(head + "static const TunedRow kTunedTable[] = {\n")
+        for (H, p, C, frames), b in sorted(table.items(), key=lambda kv: (-kv[0][0], kv[0][2], kv[0][3])):
+            f.write("    {%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %.1ff},\n"
+                    % (H, p, C, frames, b["algo"], b["row_rb"], b["row_order1"], b["row_slots"], b["row_tile_kb"],
+                       b["cube_stage_kb"], b["cube_stages"], b["cube_warps"], b.get("us", 0.0)))
+        f.write("};\n}  // namespace cp360\n")
+    with open(os.path.join(args.out, "tune_chain_log.txt"), "w") as f:
+        f.write("\n".join(log) + "\n")
+    print("wrote %d rows" % len(table))
+
+
+if __name__ == "__main__":
+    main()
