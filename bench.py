@@ -656,6 +656,10 @@ def run_chain(args, ctx):
             pipe.process_host(batches[:4], out_host[:4], **kw)          # warm-up (staging buffers, streams)
             torch.cuda.synchronize()
             ctx.barrier()
+            # upload-only ceiling with the same buffers, ring and streams, all ranks at once — taken before AND after
+            # the end-to-end run (the uplink is shared with the box's other GPUs, whose tenants come and go)
+            c0 = pipe.h2d_probe(batches)
+            ctx.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
@@ -665,10 +669,10 @@ def run_chain(args, ctx):
             torch.cuda.synchronize()
             wall.append(time.perf_counter() - t0)
             dt = ctx.max_over_ranks(e0.elapsed_time(e1) / 1e3)   # device time (CUDA events), max over ranks
-            # upload-only ceiling with the same buffers, ring and streams, all ranks at once
             ctx.barrier()
-            ceil, sec, nbytes = pipe.h2d_probe(batches)
-            return world * B * E / dt, ceil, world * nbytes / ctx.max_over_ranks(sec) / 1e9
+            c1 = pipe.h2d_probe(batches)
+            agg = [world * c[2] / ctx.max_over_ranks(c[1]) / 1e9 for c in (c0, c1)]
+            return world * B * E / dt, max(c0[0], c1[0]), max(agg)
 
         shape = (B, EQUI_H, EQUI_W, 3)
         host_u8 = host_frames(torch, args, shape, torch.uint8, 2)
@@ -688,8 +692,9 @@ def run_chain(args, ctx):
                "h2d_ceiling_gbs_rank0": round(ceil_u8, 1), "h2d_ceiling_gbs_aggregate": round(ceil_u8_sum, 1),
                "frac_of_h2d_ceiling": round(agg_gbs / ceil_u8_sum, 3),
                "h2d_ceiling_what": "the same page-locked batches through the same staging ring and copy streams, no kernels, "
-                                   "all ranks at once (SphericalPipeline.h2d_probe); aggregate = all ranks' bytes / the slowest "
-                                   "rank's time: what this box can upload at this GPU count",
+                                   "all ranks at once (SphericalPipeline.h2d_probe), before and after the end-to-end run "
+                                   "(the larger); aggregate = all ranks' bytes / the slowest rank's time: what this box can "
+                                   "upload at this GPU count",
                "device_rate_frames_per_s": round(value, 1),
                "host_alloc": args.host_alloc, "staging_depth": args.e2e_depth, "copy_streams": args.e2e_copy_streams,
                "f32_host_frames": {"value": round(v_f32, 1), "h2d_bytes_per_step": h2d_bytes * 4,

@@ -150,7 +150,8 @@ constexpr int kC2eSmallThreads = 512;
 __device__ __constant__ int kFaceSkew[6] = {0 /*B*/, 4 /*D*/, 8 /*F*/, 16 /*L*/, 24 /*R*/, 28 /*T*/};   // non-decreasing: regions stay disjoint
 constexpr int kFaceSkewMax = 32;
 
-template <int MODE>
+// TWW > 0: w*w known at compile time (49 / 64): plane strides of the unrolled channel walk become immediates
+template <int MODE, int TWW>
 __global__ void __launch_bounds__(kC2eSmallThreads)
 c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
                  const float4* __restrict__ wts, float* __restrict__ out, int C, int w, int kch,
@@ -158,7 +159,7 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float* cs = reinterpret_cast<float*>(smem_raw + 128);       // [6][kch][w*w]
-  const int P = 8 * w * w, ww = w * w;
+  const int ww = TWW ? TWW : w * w, P = 8 * ww;
   const int b = blockIdx.x / groups, gidx = blockIdx.x - b * groups;
   const int c0 = gidx * kch, kl = min(kch, C - c0);
   const int tid = threadIdx.x;
@@ -189,18 +190,21 @@ c2e_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ ta
     const bool nw_ok = xw_ok && yn_ok, ne_ok = xe_ok && yn_ok, sw_ok = xw_ok && ys_ok,
                se_ok = xe_ok && ys_ok;
     const float* src = cs + (size_t)t.face * kch * ww + kFaceSkew[t.face];
-    const int o_nw = yn * w + xw, o_ne = yn * w + xe, o_sw = ys * w + xw, o_se = ys * w + xe;
+    const float* p_nw = src + yn * w + xw;
+    const float* p_ne = src + yn * w + xe;
+    const float* p_sw = src + ys * w + xw;
+    const float* p_se = src + ys * w + xe;
     float best = -INFINITY;
     int best_c = 0;
     float* dst = out + ((int64_t)b * C + c0) * P + pix;
-#pragma unroll 4
-    for (int c = 0; c < kl; ++c, src += ww) {
+#pragma unroll 8
+    for (int c = 0; c < kl; ++c) {
       float acc = 0.0f;
-      if (nw_ok) acc = fmaf(src[o_nw], wt.x, acc);
-      if (ne_ok) acc = fmaf(src[o_ne], wt.y, acc);
-      if (sw_ok) acc = fmaf(src[o_sw], wt.z, acc);
-      if (se_ok) acc = fmaf(src[o_se], wt.w, acc);
-      if (MODE == 0) __stcs(dst + (int64_t)c * P, acc);
+      if (nw_ok) acc = fmaf(p_nw[c * ww], wt.x, acc);
+      if (ne_ok) acc = fmaf(p_ne[c * ww], wt.y, acc);
+      if (sw_ok) acc = fmaf(p_sw[c * ww], wt.z, acc);
+      if (se_ok) acc = fmaf(p_se[c * ww], wt.w, acc);
+      if (MODE == 0) __stcs(dst + c * P, acc);
       else if (MODE == 1) best = max_nan(best, acc);
       else max_update(acc, c, best, best_c);
     }
@@ -234,13 +238,18 @@ struct C2eMaxArgs {
   int stage_floats;      // 6 * K * w * w + skew
 };
 
-template <int MODE, int NPIX>
+// TWW > 0: w*w known at compile time (49 / 64, the reference's map sizes): the channel walk's plane offsets become
+// immediates. The kernel is instruction-issue bound (ncu: 62 % issue-active, 38 thread instructions per
+// pixel-channel before this), so the inner loop carries nothing it does not need: four pointers and four
+// predicates set up per stage, fmaxf / a compare for the running max, and the NaN rule of torch.max kept in a
+// separate "first NaN channel" register that is merged once at the end.
+template <int MODE, int NPIX, int TWW>
 __global__ void __launch_bounds__(kC2eSmallThreads)
 c2e_max_cluster_kernel(const C2eMaxArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int G = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
-  const int w = a.w, ww = w * w, P = 8 * ww;
+  const int w = a.w, ww = TWW ? TWW : w * w, P = 8 * ww;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                    // [stages]
   float* part_val = reinterpret_cast<float*>(smem_raw + 64);                 // [P]
   int* part_arg = reinterpret_cast<int*>(part_val + P);                      // [P] (MODE 2)
@@ -262,26 +271,28 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
     for (int f = 0; f < 6; ++f)
       tma::bulk_load(dst + (size_t)f * fstride + kFaceSkew[f], a.cube + (((int64_t)b * 6 + f) * a.C + c0) * ww, bytes, &full[s]);
   };
-  if (tid == 0) {
-    for (int s = 0; s < a.stages; ++s) tma::mbar_init(&full[s], 1);
+  if (tid < 32) {                                        // warp-uniform branch, predicated body: warp 0 never diverges here
+    if (tid < a.stages) tma::mbar_init(&full[tid], 1);
     tma::fence_mbar_init();
   }
   __syncthreads();
   pdl_wait();
   if (tid == 0)
     for (int i = 0; i < min(a.stages, n_st); ++i) issue(i);
+  __syncwarp();
 
   // this thread's pixels: plan entries live in registers for the whole kernel
   int off[NPIX][4];
   float wt[NPIX][4];
   int foff[NPIX];
   float best[NPIX];
-  int best_c[NPIX];
+  int best_c[NPIX], nan_c[NPIX];                           // nan_c: first channel whose value is NaN (INT_MAX: none)
 #pragma unroll
   for (int k = 0; k < NPIX; ++k) {
     const int pix = tid + k * kC2eSmallThreads;
     best[k] = -INFINITY;
     best_c[k] = c_begin;
+    nan_c[k] = 0x7fffffff;
     foff[k] = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { off[k][j] = 0; wt[k][j] = 0.0f; }
@@ -290,8 +301,8 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
       const float4 w4 = __ldg(a.wts + pix);
       const bool xw_ok = (unsigned)t.x0 < (unsigned)w, xe_ok = (unsigned)(t.x0 + 1) < (unsigned)w;
       const bool yn_ok = (unsigned)t.y0 < (unsigned)w, ys_ok = (unsigned)(t.y0 + 1) < (unsigned)w;
-      // out-of-face taps: address clamped into the face, weight zeroed — 0 * finite = 0 is what skipping the tap
-      // gives, and an Inf / NaN sitting at the clamped address must not leak in, so those taps are predicated below
+      // out-of-face taps (padding_mode='zeros') are skipped, not multiplied by zero: an Inf / NaN next to the face
+      // edge must not leak in. Their addresses are clamped into the face so the pointer set-up stays uniform.
       const int xw = xw_ok ? t.x0 : 0, xe = xe_ok ? t.x0 + 1 : 0, yn = yn_ok ? t.y0 : 0, ys = ys_ok ? t.y0 + 1 : 0;
       off[k][0] = yn * w + xw; off[k][1] = yn * w + xe; off[k][2] = ys * w + xw; off[k][3] = ys * w + xe;
       wt[k][0] = w4.x; wt[k][1] = w4.y; wt[k][2] = w4.z; wt[k][3] = w4.w;
@@ -310,22 +321,31 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
     for (int k = 0; k < NPIX; ++k) {
       if (NPIX > 1 && tid + k * kC2eSmallThreads >= P) break;
       const unsigned ok = (unsigned)foff[k] >> 24;
+      const bool ok0 = ok & 1u, ok1 = ok & 2u, ok2 = ok & 4u, ok3 = ok & 8u;
       const float* src = st + (foff[k] & 0xffffff);
+      const float* p0 = src + off[k][0];
+      const float* p1 = src + off[k][1];
+      const float* p2 = src + off[k][2];
+      const float* p3 = src + off[k][3];
+      const float w0 = wt[k][0], w1 = wt[k][1], w2 = wt[k][2], w3 = wt[k][3];
       float bv = best[k];
-      int bc = best_c[k];
-#pragma unroll 4
-      for (int c = 0; c < kl; ++c, src += ww) {
+      int bc = best_c[k], nc = nan_c[k];
+#pragma unroll 8
+      for (int c = 0; c < kl; ++c) {
         float acc = 0.0f;                      // order of torch's grid_sampler CUDA kernel
-        if (ok & 1u) acc = fmaf(src[off[k][0]], wt[k][0], acc);
-        if (ok & 2u) acc = fmaf(src[off[k][1]], wt[k][1], acc);
-        if (ok & 4u) acc = fmaf(src[off[k][2]], wt[k][2], acc);
-        if (ok & 8u) acc = fmaf(src[off[k][3]], wt[k][3], acc);
-        if (MODE == 1) bv = max_nan(bv, acc);
-        else max_update(acc, c0 + c, bv, bc);
+        if (ok0) acc = fmaf(p0[c * ww], w0, acc);
+        if (ok1) acc = fmaf(p1[c * ww], w1, acc);
+        if (ok2) acc = fmaf(p2[c * ww], w2, acc);
+        if (ok3) acc = fmaf(p3[c * ww], w3, acc);
+        if (acc != acc) nc = min(nc, c0 + c);
+        if (MODE == 1) bv = fmaxf(bv, acc);    // ignores a NaN operand: NaNs are carried by nc
+        else if (acc > bv) { bv = acc; bc = c0 + c; }
       }
       best[k] = bv;
       best_c[k] = bc;
+      nan_c[k] = nc;
     }
+    __syncwarp();                                        // reconverge lane 0 (bulk-load issue) before the block barrier
     __syncthreads();                                     // every thread is done with stage s
     if (tid == 0 && i + a.stages < n_st) issue(i + a.stages);
   }
@@ -333,8 +353,9 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
   for (int k = 0; k < NPIX; ++k) {
     const int pix = tid + k * kC2eSmallThreads;
     if (pix < P) {
-      part_val[pix] = best[k];
-      if (MODE == 2) part_arg[pix] = best_c[k];
+      const bool has_nan = nan_c[k] != 0x7fffffff;       // torch.max: a NaN wins, the first NaN channel is the arg-max
+      part_val[pix] = has_nan ? __int_as_float(0x7fc00000) : best[k];
+      if (MODE == 2) part_arg[pix] = has_nan ? nan_c[k] : best_c[k];
     }
   }
   cluster.sync();                                        // all G partial maps are in place (release / acquire)
@@ -411,9 +432,8 @@ c2e_bwd_small_kernel(const C2eBwdArgs a) {
     tma::mbar_expect_tx(&full[i & 1], bytes);
     tma::bulk_load(ring + (size_t)(i & 1) * KCH * P, a.gequi + ((int64_t)b * a.C + c0) * P, bytes, &full[i & 1]);
   };
-  if (tid == 0) {
-    tma::mbar_init(&full[0], 1);
-    tma::mbar_init(&full[1], 1);
+  if (tid < 32) {                                        // warp-uniform branch, predicated body
+    if (tid < 2) tma::mbar_init(&full[tid], 1);
     tma::fence_mbar_init();
   }
   __syncthreads();
@@ -441,6 +461,7 @@ c2e_bwd_small_kernel(const C2eBwdArgs a) {
       for (int c = 0; c < KCH; ++c)
         if (c < kl) __stcs(dst + (int64_t)c * ww, acc[c]);
     }
+    __syncwarp();                                        // reconverge lane 0 (bulk-load issue) before the block barrier
     __syncthreads();                                     // every thread is done with ring[i & 1]
     if (tid == 0 && i + 2 < n_mine) issue(i + 2);
   }
@@ -753,7 +774,7 @@ static int launch_c2e(const float* cube, const uint32_t* taps, const float* wts,
     smem = 128 + (size_t)6 * k * ww * 4 + kFaceSkewMax * 4;
     const int groups = (int)((C + k - 1) / k);
     CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
-    auto kern = c2e_small_kernel<MODE>;
+    auto kern = ww == 64 ? c2e_small_kernel<MODE, 64> : ww == 49 ? c2e_small_kernel<MODE, 49> : c2e_small_kernel<MODE, 0>;
     CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_kernel(kern, (unsigned)(B * groups), kC2eSmallThreads, smem, st, cube, taps, reinterpret_cast<const float4*>(wts), out, (int)C, w, k, groups);
     CP360_LAUNCHED();
@@ -786,6 +807,7 @@ static bool try_c2e_max_cluster(const float* cube, const uint32_t* taps, const f
   a.C = (int)C; a.w = w;
   a.K = std::max(q, (int)((24 * 1024) / (6 * ww * 4)) / q * q);
   int G = 8;
+  if (const char* v = getenv("CP360_C2E_CLUSTER_SIZE")) G = std::max(1, std::min(8, atoi(v)));   // experiments (power of two)
   while (G > 1 && (B * G > 4 * (int64_t)sm_count() || (C + G - 1) / G < a.K)) G >>= 1;   // enough CTAs, >= one stage each
   a.Cg = (int)(((C + G - 1) / G + q - 1) / q * q);
   a.K = std::min(a.K, a.Cg);
@@ -794,7 +816,10 @@ static bool try_c2e_max_cluster(const float* cube, const uint32_t* taps, const f
   a.ring_off = (64 + 8 * P + 127) & ~127;
   const size_t smem = (size_t)a.ring_off + (size_t)a.stages * a.stage_floats * 4;
   if (smem > 200 * 1024) return false;
-  void (*kern)(const C2eMaxArgs) = P <= kC2eSmallThreads ? c2e_max_cluster_kernel<MODE, 1> : c2e_max_cluster_kernel<MODE, kC2eMaxPix>;
+  void (*kern)(const C2eMaxArgs) = ww == 64   ? c2e_max_cluster_kernel<MODE, 1, 64>
+                                   : ww == 49 ? c2e_max_cluster_kernel<MODE, 1, 49>
+                                   : P <= kC2eSmallThreads ? c2e_max_cluster_kernel<MODE, 1, 0>
+                                                           : c2e_max_cluster_kernel<MODE, kC2eMaxPix, 0>;
   if (P > kC2eSmallThreads * kC2eMaxPix) return false;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
