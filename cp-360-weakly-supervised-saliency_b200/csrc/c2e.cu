@@ -395,37 +395,68 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
 //   c2e_bwd_small_kernel  w <= 16: CTA r of a frame walks the channel groups r, r + G, ...; the transposed plan is
 //                         copied to shared memory once per CTA (16-bit offsets / pixel ids), the gradient planes of
 //                         a group arrive by one TMA bulk copy each into a two-stage ring.
+//                         Contributor counts are very uneven (a pole pixel of the top face collects 46 equi pixels
+//                         at w = 8, 90 at w = 16; the mean is 5), so a cube pixel with more than kC2eBwdSplit
+//                         contributors is split over a team of 2..32 adjacent lanes whose partial sums meet in a
+//                         fixed shuffle tree: every warp walks at most ~kC2eBwdSplit contributors per pass and the
+//                         summation order stays fixed. The slot table (one word per lane-slot: pixel, position in
+//                         the team, log2 team size; teams of one size are contiguous and every size class starts on
+//                         a warp boundary) is built per CTA by a block scan.
 //   c2e_bwd_gather_kernel any w: contributors and gradients read through the read-only path.
+constexpr int kC2eBwdSplit = 8;
+constexpr int kC2eBwdClasses = 6;                        // team sizes 1, 2, 4, 8, 16, 32
+
 struct C2eBwdArgs {
   const float* gequi;
   const int32_t* offs;
   const int32_t* pix;
   const float* wts;
   float* gcube;
-  int C, w, G, n_entries;
-  int pix_off, wts_off, ring_off;      // byte offsets in dynamic shared memory (offs at 64)
+  int C, w, G, n_entries, slot_cap, split, order;
+  int slot_off, pix_off, wts_off, ring_off;    // byte offsets in dynamic shared memory (offs at 256)
 };
 
-template <int KCH>
+__device__ __forceinline__ int c2e_bwd_class(int cnt, int split) {
+  int ls = 0;
+  while (ls < kC2eBwdClasses - 1 && ((cnt + (1 << ls) - 1) >> ls) > split) ++ls;
+  return ls;
+}
+
+// walk order of the cube pixels when slots are handed out: 1 = row by row across the four equatorial faces (0, 2, 3, 4
+// in this cube layout), so that the 32 lanes of a warp read 32 different equi columns (= shared-memory banks at w = 8)
+__device__ __forceinline__ int c2e_bwd_walk(int q, int w, int ww, int order) {
+  if (order == 0 || q >= 5 * ww) return q;
+  if (q >= 4 * ww) return q - 3 * ww;                    // face 1 after the equatorial ring
+  const int row = q / (4 * w), rem = q - row * 4 * w, fi = rem / w, col = rem - fi * w;
+  return (fi == 0 ? 0 : fi + 1) * ww + row * w + col;
+}
+
+template <int KCH, int TW>                               // TW: compile-time face width (0 = a.w) -> immediate plane strides
 __global__ void __launch_bounds__(kC2eSmallThreads)
 c2e_bwd_small_kernel(const C2eBwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                  // [2]
-  uint16_t* offs_s = reinterpret_cast<uint16_t*>(smem_raw + 64);           // [NC + 1]
+  int* n_slots_s = reinterpret_cast<int*>(smem_raw + 16);                  // padded slot count
+  unsigned long long* scan_lo = reinterpret_cast<unsigned long long*>(smem_raw + 64);   // [16] warp totals, classes 0..3
+  uint32_t* scan_hi = reinterpret_cast<uint32_t*>(smem_raw + 192);         // [16] classes 4, 5
+  uint16_t* offs_s = reinterpret_cast<uint16_t*>(smem_raw + 256);          // [NC + 1]
+  uint32_t* slot_s = reinterpret_cast<uint32_t*>(smem_raw + a.slot_off);   // [slot_cap]
   uint16_t* pix_s = reinterpret_cast<uint16_t*>(smem_raw + a.pix_off);     // [n_entries]
   float* wts_s = reinterpret_cast<float*>(smem_raw + a.wts_off);           // [n_entries]
   float* ring = reinterpret_cast<float*>(smem_raw + a.ring_off);           // [2][KCH][P]
-  const int w = a.w, ww = w * w, P = 8 * ww, NC = 6 * ww;
+  const int w = TW ? TW : a.w, ww = w * w, P = 8 * ww, NC = 6 * ww;
   const int b = blockIdx.x / a.G, r = blockIdx.x - b * a.G;
   const int groups = (a.C + KCH - 1) / KCH;
   const int n_mine = r < groups ? (groups - r + a.G - 1) / a.G : 0;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int kWarps = kC2eSmallThreads / 32;
   pdl_trigger();
   for (int i = tid; i <= NC; i += kC2eSmallThreads) offs_s[i] = (uint16_t)__ldg(a.offs + i);
   for (int i = tid; i < a.n_entries; i += kC2eSmallThreads) {
     pix_s[i] = (uint16_t)__ldg(a.pix + i);
     wts_s[i] = __ldg(a.wts + i);
   }
+  for (int i = tid; i < a.slot_cap; i += kC2eSmallThreads) slot_s[i] = 0xffffffffu;
   auto issue = [&](int i) {                                                 // thread 0: the CTA's i-th group
     const int c0 = (r + i * a.G) * KCH, kl = min(KCH, a.C - c0);
     const uint32_t bytes = (uint32_t)(kl * P) * 4u;
@@ -440,26 +471,102 @@ c2e_bwd_small_kernel(const C2eBwdArgs a) {
   pdl_wait();
   if (tid == 0)
     for (int i = 0; i < min(2, n_mine); ++i) issue(i);
+  __syncwarp();
+
+  // ---- slot table: thread t owns the cube pixels [t * cpt, (t + 1) * cpt); an exclusive block scan of the per-class
+  // pixel counts (16-bit fields: NC <= 1536) gives every pixel its rank inside its class in natural order
+  const int cpt = (NC + kC2eSmallThreads - 1) / kC2eSmallThreads;
+  unsigned long long lo = 0;
+  uint32_t hi = 0;
+  for (int i = 0; i < cpt; ++i) {
+    const int q = tid * cpt + i;
+    if (q < NC) {
+      const int cell = c2e_bwd_walk(q, w, ww, a.order);
+      const int ls = c2e_bwd_class((int)offs_s[cell + 1] - (int)offs_s[cell], a.split);
+      if (ls < 4) lo += 1ull << (16 * ls); else hi += 1u << (16 * (ls - 4));
+    }
+  }
+  unsigned long long inc_lo = lo;
+  uint32_t inc_hi = hi;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t_lo = __shfl_up_sync(0xffffffffu, inc_lo, d);
+    const uint32_t t_hi = __shfl_up_sync(0xffffffffu, inc_hi, d);
+    if (lane >= d) { inc_lo += t_lo; inc_hi += t_hi; }
+  }
+  if (lane == 31) { scan_lo[wid] = inc_lo; scan_hi[wid] = inc_hi; }
+  __syncthreads();
+  unsigned long long pre_lo = inc_lo - lo, tot_lo = 0;
+  uint32_t pre_hi = inc_hi - hi, tot_hi = 0;
+  for (int k = 0; k < kWarps; ++k) {
+    if (k < wid) { pre_lo += scan_lo[k]; pre_hi += scan_hi[k]; }
+    tot_lo += scan_lo[k]; tot_hi += scan_hi[k];
+  }
+  int base[kC2eBwdClasses + 1];
+  base[0] = 0;
+#pragma unroll
+  for (int ls = 0; ls < kC2eBwdClasses; ++ls) {
+    const int n = ls < 4 ? (int)((tot_lo >> (16 * ls)) & 0xffffu) : (int)((tot_hi >> (16 * (ls - 4))) & 0xffffu);
+    base[ls + 1] = base[ls] + (((n << ls) + 31) & ~31);
+  }
+  if (tid == 0) *n_slots_s = base[kC2eBwdClasses];
+  for (int i = 0; i < cpt; ++i) {
+    const int q = tid * cpt + i;
+    if (q < NC) {
+      const int cell = c2e_bwd_walk(q, w, ww, a.order);
+      const int ls = c2e_bwd_class((int)offs_s[cell + 1] - (int)offs_s[cell], a.split);
+      const int rank = ls < 4 ? (int)((pre_lo >> (16 * ls)) & 0xffffu) : (int)((pre_hi >> (16 * (ls - 4))) & 0xffffu);
+      if (ls < 4) pre_lo += 1ull << (16 * ls); else pre_hi += 1u << (16 * (ls - 4));
+      int bs = 0;
+#pragma unroll
+      for (int k = 0; k < kC2eBwdClasses; ++k) if (k == ls) bs = base[k];
+      const int s0 = bs + (rank << ls);
+      for (int j = 0; j < (1 << ls); ++j) slot_s[s0 + j] = (uint32_t)cell | ((uint32_t)j << 11) | ((uint32_t)ls << 16);
+    }
+  }
+  __syncthreads();
+  const int n_slots = *n_slots_s;
+
   for (int i = 0; i < n_mine; ++i) {
     tma::mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
     const int c0 = (r + i * a.G) * KCH, kl = min(KCH, a.C - c0);
     const float* gs = ring + (size_t)(i & 1) * KCH * P;
-    for (int cell = tid; cell < NC; cell += kC2eSmallThreads) {
+    for (int s0 = wid * 32; s0 < n_slots; s0 += kC2eSmallThreads) {
+      const uint32_t info = slot_s[s0 + lane];
+      const bool valid = info != 0xffffffffu;
+      const int ls = (int)(__shfl_sync(0xffffffffu, info, 0) >> 16);       // a chunk holds one class; its lane 0 is never padding
+      const int cell = valid ? (int)(info & 0x7ffu) : 0, j = (int)((info >> 11) & 31u);
+      int e0 = 0, e1 = 0;                                // lane j of a team takes contributors j, j + s, j + 2s, ...
+      if (valid) {
+        e0 = (int)offs_s[cell] + j;
+        e1 = offs_s[cell + 1];
+      }
+      const int es = 1 << ls;
       float acc[KCH];
 #pragma unroll
       for (int c = 0; c < KCH; ++c) acc[c] = 0.0f;
-      const int e0 = offs_s[cell], e1 = offs_s[cell + 1];
-      for (int e = e0; e < e1; ++e) {
+      for (int e = e0; e < e1; e += es) {
         const float* g = gs + pix_s[e];
         const float wt = wts_s[e];
 #pragma unroll
-        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(g[c * P], wt, acc[c]);   // rows beyond kl hold stale finite data; never stored
+        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(g[c * P], wt, acc[c]);   // rows beyond kl hold stale data; never stored
       }
-      const int f = cell / ww, rr = cell - f * ww;
-      float* dst = a.gcube + (((int64_t)b * 6 + f) * a.C + c0) * ww + rr;
+      for (int d = (1 << ls) >> 1; d > 0; d >>= 1) {     // fixed tree over the team; lane j == 0 ends with the sum
 #pragma unroll
-      for (int c = 0; c < KCH; ++c)
-        if (c < kl) __stcs(dst + (int64_t)c * ww, acc[c]);
+        for (int c = 0; c < KCH; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], d);
+      }
+      if (valid && j == 0) {
+        const int f = cell / ww, rr = cell - f * ww;
+        float* dst = a.gcube + (((int64_t)b * 6 + f) * a.C + c0) * ww + rr;
+        if (kl == KCH) {
+#pragma unroll
+          for (int c = 0; c < KCH; ++c) __stcs(dst + c * ww, acc[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < KCH; ++c)
+            if (c < kl) __stcs(dst + c * ww, acc[c]);
+        }
+      }
     }
     __syncwarp();                                        // reconverge lane 0 (bulk-load issue) before the block barrier
     __syncthreads();                                     // every thread is done with ring[i & 1]
@@ -600,17 +707,34 @@ __device__ __forceinline__ void cubic_pixel(const float* __restrict__ src, float
   }
 }
 
-// w <= 16: same staging as c2e_small_kernel (block = (b, channel group), six bulk copies)
+// w <= 16: same staging as c2e_small_kernel (block = (b, channel group), six bulk copies). A warp whose lanes mix
+// windows inside the face (row-by-row sum) with windows on a border (tap-by-tap sum) executes both code paths for
+// every channel — and at w = 8 every run of 32 consecutive equi pixels mixes them. The pixels are therefore handed to
+// the lanes in a sorted order (inside windows first, then border windows, each in raster order; built per CTA with
+// ballots while the bulk copies are in flight), so all but one warp run a single path. TW = compile-time face width
+// (0: run-time), which turns the row / plane strides of the 16 taps into immediates.
+__device__ __forceinline__ bool cubic_inside(const CubicTap t, int w) {
+  const int lim = max(w - 3, 0);
+  return (unsigned)t.x0 < (unsigned)lim && (unsigned)t.y0 < (unsigned)lim;
+}
+
+constexpr int kCubicMaxRounds = 4;                        // P = 8 w^2 <= 2048 pixels in rounds of kC2eSmallThreads
+
+template <int TW>
 __global__ void __launch_bounds__(kC2eSmallThreads)
 c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restrict__ taps,
-                       float* __restrict__ out, int C, int w, int kch, int groups) {
+                       float* __restrict__ out, int C, int w_rt, int kch, int groups, int order_off) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  float* cs = reinterpret_cast<float*>(smem_raw + 128);       // [6][kch][w*w]
+  uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + 16);             // [kCubicMaxRounds][16 warps] inside windows
+  float* cs = reinterpret_cast<float*>(smem_raw + 256);      // [6][kch][w*w]
+  uint16_t* order_s = reinterpret_cast<uint16_t*>(smem_raw + order_off);    // [P]
+  const int w = TW ? TW : w_rt;
   const int P = 8 * w * w, ww = w * w;
   const int b = blockIdx.x / groups, gidx = blockIdx.x - b * groups;
   const int c0 = gidx * kch, kl = min(kch, C - c0);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int kWarps = kC2eSmallThreads / 32;
   pdl_trigger();
   pdl_wait();
   if (tid == 0) {
@@ -622,9 +746,40 @@ c2e_cubic_small_kernel(const float* __restrict__ cube, const uint32_t* __restric
     for (int f = 0; f < 6; ++f)
       tma::bulk_load(cs + (size_t)f * kch * ww + kFaceSkew[f], cube + (((int64_t)b * 6 + f) * C + c0) * ww, bytes, bar);
   }
+  __syncwarp();
+  const int rounds = (P + kC2eSmallThreads - 1) / kC2eSmallThreads;
+  unsigned in_mask[kCubicMaxRounds];
+#pragma unroll
+  for (int r = 0; r < kCubicMaxRounds; ++r) {
+    in_mask[r] = 0;
+    if (r < rounds) {
+      const int pix = r * kC2eSmallThreads + tid;
+      const bool in = pix < P && cubic_inside(decode_cubic_tap(__ldg(taps + pix)), w);
+      in_mask[r] = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) cnt_s[r * kWarps + wid] = (uint16_t)__popc(in_mask[r]);
+    }
+  }
+  __syncthreads();
+  int n_in = 0;
+  for (int k = 0; k < rounds * kWarps; ++k) n_in += cnt_s[k];
+#pragma unroll
+  for (int r = 0; r < kCubicMaxRounds; ++r) {
+    if (r < rounds) {
+      const int first = r * kC2eSmallThreads + wid * 32, pix = first + lane;   // the warp's 32 pixels of this round
+      int before_in = 0;                                 // inside windows among the pixels before `first`
+      for (int k = 0; k < r * kWarps + wid; ++k) before_in += cnt_s[k];
+      const unsigned lt = (1u << lane) - 1u;
+      if (pix < P) {
+        const int pos = ((in_mask[r] >> lane) & 1u) ? before_in + __popc(in_mask[r] & lt)
+                                                    : n_in + (first - before_in) + __popc(~in_mask[r] & lt);
+        order_s[pos] = (uint16_t)pix;
+      }
+    }
+  }
   __syncthreads();
   tma::mbar_wait(bar, 0);
-  for (int pix = tid; pix < P; pix += kC2eSmallThreads) {
+  for (int idx = tid; idx < P; idx += kC2eSmallThreads) {
+    const int pix = order_s[idx];
     const CubicTap t = decode_cubic_tap(__ldg(taps + pix));
     cubic_pixel(cs + (size_t)t.face * kch * ww + kFaceSkew[t.face], out + ((int64_t)b * C + c0) * P + pix, t, w, ww, P, kl);
   }
@@ -945,12 +1100,15 @@ int cp360_c2e_cubic_fwd(const float* cube, const uint32_t* taps, float* equi, in
     int q = 1;
     while ((q * ww) % 4) q <<= 1;
     while (k > 4 * q && B * ((C + k - 1) / k) < 2 * (int64_t)sm_count()) k = std::max(q, (k / 2) - ((k / 2) % q));
-    smem = 128 + (size_t)6 * k * ww * 4 + kFaceSkewMax * 4;
+    if (const char* e = std::getenv("CP360_CUBIC_K")) k = std::max(q, std::min(k, std::atoi(e) / q * q));   // experiments
+    const int order_off = (int)((256 + ((size_t)6 * k * ww + kFaceSkewMax) * 4 + 15) & ~(size_t)15);
+    smem = (size_t)order_off + (size_t)P * 2;
     const int groups = (int)((C + k - 1) / k);
     CP360_CHECK_ARG(B * groups < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
-    CP360_CUDA_OK(cudaFuncSetAttribute(c2e_cubic_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_kernel(c2e_cubic_small_kernel, (unsigned)(B * groups), kC2eSmallThreads, smem, st, cube, taps, equi,
-                  (int)C, w, k, groups);
+    void (*kern)(const float*, const uint32_t*, float*, int, int, int, int, int) =
+        w == 8 ? c2e_cubic_small_kernel<8> : w == 7 ? c2e_cubic_small_kernel<7> : c2e_cubic_small_kernel<0>;
+    CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(kern, (unsigned)(B * groups), kC2eSmallThreads, smem, st, cube, taps, equi, (int)C, w, k, groups, order_off);
     CP360_LAUNCHED();
     return CP360_OK;
   }
@@ -977,22 +1135,37 @@ int cp360_c2e_bwd(const float* gequi, const int32_t* offs, const int32_t* pix, c
   if (rc != CP360_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = 8 * w * w, NC = 6 * w * w;
-  const bool small = w <= 16 && ((uintptr_t)gequi % 16) == 0 && n_entries <= 65535;   // 16-bit ids in shared memory
+  const char* sw = getenv("CP360_C2E_BWD_SMALL");        // "0": the read-only-path gather for every w (A/B, racecheck_probe.py)
+  const bool small = w <= 16 && ((uintptr_t)gequi % 16) == 0 && n_entries <= 65535 && !(sw && *sw == '0');   // 16-bit ids in shared memory
   if (small) {
     C2eBwdArgs a;
     a.gequi = gequi; a.offs = offs; a.pix = pix; a.wts = bwts; a.gcube = gcube; a.C = (int)C; a.w = w;
     a.n_entries = n_entries;
     const int kch = w <= 8 ? 16 : 8;
     const int64_t groups = (C + kch - 1) / kch;
-    a.G = (int)std::max<int64_t>(1, std::min<int64_t>(groups, (3 * (int64_t)sm_count() + B - 1) / B));
-    a.pix_off = (64 + 2 * (NC + 1) + 15) & ~15;
+    a.split = kC2eBwdSplit;
+    a.order = 1;
+    if (const char* e = std::getenv("CP360_C2E_BWD_SPLIT")) a.split = std::max(2, std::min(64, std::atoi(e)));   // experiments
+    if (const char* e = std::getenv("CP360_C2E_BWD_ORDER")) a.order = std::atoi(e) != 0;
+    a.slot_cap = NC + 2 * n_entries / a.split + 32 * kC2eBwdClasses;   // teams: sum of sizes < NC + 2 * entries / split
+    a.slot_off = (256 + 2 * (NC + 1) + 15) & ~15;
+    a.pix_off = a.slot_off + 4 * a.slot_cap;
     a.wts_off = (a.pix_off + 2 * n_entries + 15) & ~15;
     a.ring_off = (a.wts_off + 4 * n_entries + 127) & ~127;
     const size_t smem = (size_t)a.ring_off + (size_t)2 * kch * P * 4;
-    CP360_CHECK_ARG(B * a.G < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
     if (smem <= 200 * 1024) {
-      void (*kern)(const C2eBwdArgs) = kch == 16 ? c2e_bwd_small_kernel<16> : c2e_bwd_small_kernel<8>;
+      void (*kern)(const C2eBwdArgs) = w == 8    ? c2e_bwd_small_kernel<16, 8>       // the reference's 224 / 256 px score maps
+                                       : w == 7  ? c2e_bwd_small_kernel<16, 7>
+                                       : w == 16 ? c2e_bwd_small_kernel<8, 16>
+                                       : w == 14 ? c2e_bwd_small_kernel<8, 14>
+                                       : kch == 16 ? c2e_bwd_small_kernel<16, 0> : c2e_bwd_small_kernel<8, 0>;
       CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;                                     // one resident wave: CTA r of a frame walks groups r, r + G, ...
+      CP360_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kC2eSmallThreads, smem));
+      const int64_t slots = (int64_t)sm_count() * std::max(1, per_sm);
+      a.G = (int)std::max<int64_t>(1, std::min<int64_t>(groups, slots / B));
+      if (const char* e = std::getenv("CP360_C2E_BWD_G")) a.G = (int)std::max<int64_t>(1, std::min<int64_t>(groups, std::atoi(e)));
+      CP360_CHECK_ARG(B * a.G < 0x7fffffff, CP360_ERR_RANGE, "grid too large");
       launch_kernel(kern, (unsigned)(B * a.G), kC2eSmallThreads, smem, st, a);
       CP360_LAUNCHED();
       return CP360_OK;

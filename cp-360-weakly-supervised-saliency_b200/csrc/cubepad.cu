@@ -551,7 +551,7 @@ static bool cube2_plan(const CubePadGeom& g, int64_t n_faces, int C, Cube2Args* 
   a->work = nullptr;
   a->out_C = C; a->out_coff = 0; a->scale = nullptr; a->shift = nullptr; a->relu = 0;
   a->stage_words = 6 * kmax * HW;
-  a->lut_off = 3 * kCubeMaxStages * 8;
+  a->lut_off = 3 * kCubeMaxStages * 8 + 16;                   // barriers, staged chunk ids, border-list length
   a->epi_off = (a->lut_off + 6 * HoWo * 4 + 15) & ~15;
   const bool epi = t_fused && (t_fused->scale || t_fused->shift || t_fused->relu);
   a->ring_off = (a->epi_off + (epi ? stages * 2 * kmax * 4 : 0) + 127) & ~127;
@@ -658,10 +658,11 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
         }
     if (max_cnt > 15) return false;
   }
-  a->lut_off = 3 * kCubeMaxStages * 8;
+  a->lut_off = 3 * kCubeMaxStages * 8 + 16;                   // barriers, staged chunk ids, border-list length
   a->ent_off = (a->lut_off + 6 * HW * 4 + 15) & ~15;
   a->ring_off = (a->ent_off + 6 * (HoWo - HW) * 2 + 127) & ~127;
   a->d_HW = make_fastdiv((uint32_t)HW);
+  a->reg_pos = env_int("CP360_BWD_REG_POS", 1);
   size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
   while (smem > 220 * 1024 && stages > 2) {
     --stages;

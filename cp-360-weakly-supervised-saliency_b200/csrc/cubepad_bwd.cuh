@@ -38,7 +38,11 @@ struct CubeBwdArgs {
   int32_t ent_off;      // byte offset of the halo lists (uint16 [6*(Ho*Wo - H*W)], staged word of channel 0)
   int32_t ring_off;     // byte offset of the staging ring
   FastDiv d_HW;         // e / (H*W)
+  int32_t reg_pos;      // 0: never use the register-cached position walk (A/B)
 };
+
+constexpr int kBwdRegPos = 12;   // positions per consumer thread that the register-cached walk holds (6*32*32 / 512)
+constexpr int kBwdRegTK = 2;     // ... used when a stage holds at most this many channels (faces of 25..32 px)
 
 // TK > 0: kmax known at compile time (the channel walk of a full chunk is unrolled in batches of 8)
 template <int TK>
@@ -60,6 +64,39 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   const int pm = max(max(g.pl, g.pr), max(g.pt, g.pd));
 
   pdl_trigger();
+  // ---- producer state (thread 0). Dynamic dealing: the first chunk of a CTA is its own index (no round trip to the
+  // counter in front of the first load), every further one gridDim.x + a ticket drawn one step ahead of its use
+  int ps = 0;
+  uint32_t pph = 0, ticket = blockIdx.x;
+  int64_t pit = 0;
+  bool pdone = false;
+  auto produce = [&]() {                               // stage one chunk (or the end mark)
+    if (pit >= a.stages) tma::mbar_wait(&empty[ps], pph ^ 1u);
+    int64_t q = (int64_t)blockIdx.x + pit * gridDim.x;
+    if (a.work) {
+      q = (int64_t)ticket;
+      if (q < a.n_chunks) ticket = gridDim.x + atomicAdd(a.work, 1u);
+    }
+    if (q >= a.n_chunks) {
+      chunk_of[ps] = -1;
+      tma::mbar_arrive(&full[ps]);                     // completes the phase: consumers see the end mark
+      pdone = true;
+      return;
+    }
+    chunk_of[ps] = q;
+    const int64_t n = q / a.cblocks;
+    const int c0 = (int)(q - n * a.cblocks) * kmax;
+    const int kl = min(kmax, a.C - c0);
+    const uint32_t bytes = (uint32_t)(kl * HoWo) * 4u;
+    tma::mbar_expect_tx(&full[ps], 6u * bytes);
+    float* dst = const_cast<float*>(ring) + (size_t)ps * a.stage_words;
+    const float* src = a.gy + ((n * 6) * a.C + c0) * HoWo;
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      tma::bulk_load(dst + f * fstride, src + (int64_t)f * a.C * HoWo, bytes, &full[ps]);
+    ++pit;
+    if (++ps == a.stages) { ps = 0; pph ^= 1u; }
+  };
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       tma::mbar_init(&full[s], 1);
@@ -74,15 +111,42 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
 #endif
     }
     tma::fence_mbar_init();
+    // the first stages - 1 chunks stream in while the tables below are built; the last stage is their scratch
+    pdl_wait();
+    for (int i = 0; i + 1 < a.stages && !pdone; ++i) produce();
   }
-  // ---- tables. Pass 1: halo copies per input position (only pixels within a pad width of a face edge have any:
-  // skip the plate walk elsewhere — at H = 32 that is 88 % of the positions)
-  for (int e = tid; e < n_in; e += blockDim.x) {
+  __syncwarp();
+  // ---- tables. Only pixels within a pad width of a face edge receive halo copies (at H = 32: 12 % of the positions,
+  // two lanes of every warp of a raster walk): they are first compacted into a list (in the idle last stage), so the
+  // plate walks below run on full warps.
+  uint16_t* blist = reinterpret_cast<uint16_t*>(const_cast<float*>(ring) + (size_t)(a.stages - 1) * a.stage_words);
+  int* n_border = reinterpret_cast<int*>(chunk_of + kCubeMaxStages);
+  if (tid == 0) *n_border = 0;
+  __syncthreads();
+  for (int e0 = warp * 32; e0 < n_in; e0 += (int)blockDim.x) {
+    const int e = e0 + lane;
+    bool border = false;
+    if (e < n_in) {
+      const int f = e / HW, r = e - f * HW;
+      const int y = r / g.W, x = r - y * g.W;
+      border = min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) < pm;
+      lut[e] = 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, border);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(n_border, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (border) blist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)e;
+  }
+  __syncthreads();
+  const int nb = *n_border;
+  // Pass 1: halo copies per border position
+  for (int i = tid; i < nb; i += blockDim.x) {
+    const int e = blist[i];
     const int f = e / HW, r = e - f * HW;
     const int y = r / g.W, x = r - y * g.W;
     int cnt = 0;
-    if (min(min(y, g.H - 1 - y), min(x, g.W - 1 - x)) < pm)
-      cubepad_for_each_copy(g, f, y, x, [&](int, int, int) { ++cnt; });
+    cubepad_for_each_copy(g, f, y, x, [&](int, int, int) { ++cnt; });
     lut[e] = (uint32_t)cnt;
   }
   __syncthreads();
@@ -105,57 +169,32 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     }
   }
   __syncthreads();
-  // Pass 2: the halo lists and the final position words
+  // Pass 2: the halo lists, then the final position words
+  for (int i = tid; i < nb; i += blockDim.x) {
+    const int e = blist[i];
+    const int f = e / HW, r = e - f * HW;
+    const int y = r / g.W, x = r - y * g.W;
+    int o = (int)(lut[e] & 0xffffu);
+    cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
+      ent[o++] = (uint16_t)(dface * fstride + oy * g.Wo + ox);
+    });
+  }
+  __syncthreads();                                     // the list starts above are read before the words change format
   for (int e = tid; e < n_in; e += blockDim.x) {
     const int f = e / HW, r = e - f * HW;
     const int y = r / g.W, x = r - y * g.W;
     const uint32_t sc = lut[e];
     const int start = (int)(sc & 0xffffu), cnt = (int)(sc >> 16);
-    if (cnt) {
-      int o = start;
-      cubepad_for_each_copy(g, f, y, x, [&](int dface, int oy, int ox) {
-        ent[o++] = (uint16_t)(dface * fstride + oy * g.Wo + ox);
-      });
-    }
     const uint32_t inner = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
     lut[e] = inner | (uint32_t)cnt << 16 | (uint32_t)start << 20;
   }
-  __syncthreads();
+  __syncthreads();                                     // also: every read of the scratch list is done before stage stages-1 is loaded
   pdl_wait();
 
   if (warp == 0) {
     // ---------------- producer: draw chunks, stage them `stages` deep
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      // dynamic dealing: the first chunk of a CTA is its own index (no round trip to the counter in front of
-      // the first load), every further one gridDim.x + a ticket drawn one step ahead of its use
-      uint32_t ticket = blockIdx.x;
-      for (int64_t it = 0;; ++it) {
-        if (it >= a.stages) tma::mbar_wait(&empty[s], ph ^ 1u);
-        int64_t q = (int64_t)blockIdx.x + it * gridDim.x;
-        if (a.work) {
-          q = (int64_t)ticket;
-          if (q < a.n_chunks) ticket = gridDim.x + atomicAdd(a.work, 1u);
-        }
-        if (q >= a.n_chunks) {
-          chunk_of[s] = -1;
-          tma::mbar_arrive(&full[s]);                  // completes the phase: consumers see the end mark
-          break;
-        }
-        chunk_of[s] = q;
-        const int64_t n = q / a.cblocks;
-        const int c0 = (int)(q - n * a.cblocks) * kmax;
-        const int kl = min(kmax, a.C - c0);
-        const uint32_t bytes = (uint32_t)(kl * HoWo) * 4u;
-        tma::mbar_expect_tx(&full[s], 6u * bytes);
-        float* dst = const_cast<float*>(ring) + (size_t)s * a.stage_words;
-        const float* src = a.gy + ((n * 6) * a.C + c0) * HoWo;
-#pragma unroll
-        for (int f = 0; f < 6; ++f)
-          tma::bulk_load(dst + f * fstride, src + (int64_t)f * a.C * HoWo, bytes, &full[s]);
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
-      }
+      while (!pdone) produce();
       if (a.work && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {   // last CTA: hand the pair back zeroed
         a.work[0] = 0;
         a.work[1] = 0;
@@ -164,10 +203,25 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     }
     return;
   }
-
   // ---------------- consumers
   const int ctid = tid - 32;
   const int64_t CHW = (int64_t)a.C * HW;
+  const bool reg_cached = TK > 0 && TK <= kBwdRegTK && n_in <= kBwdRegPos * n_cons && a.reg_pos != 0;
+  uint32_t pos_lut[kBwdRegPos];
+  int pos_dst[kBwdRegPos];                              // destination offset inside the cube's block (< 2^31: host check), -1: none
+  if (TK > 0 && TK <= kBwdRegTK) {
+#pragma unroll
+    for (int k = 0; k < kBwdRegPos; ++k) {
+      const int e = ctid + k * n_cons;
+      pos_lut[k] = 0;
+      pos_dst[k] = -1;
+      if (reg_cached && e < n_in) {
+        const int f = fdiv(e, a.d_HW);
+        pos_lut[k] = lut[e];
+        pos_dst[k] = f * (int)CHW + (e - f * HW);
+      }
+    }
+  }
   int s = 0;
   uint32_t ph = 0;
   while (true) {
@@ -179,7 +233,38 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     const int kl = min(kmax, a.C - c0);
     const float* in_s = ring + (size_t)s * a.stage_words;
     float* __restrict__ out = a.gx + ((n * 6) * a.C + c0) * HW;
-    if (TK > 0 && kl == TK) {
+    if (TK > 0 && TK <= kBwdRegTK && kl == TK && reg_cached) {
+      // few channels per stage (32x32 faces: 2): the per-position words above cost more than the data moves,
+      // so they live in registers across chunks (every thread owns the same positions in every chunk)
+      constexpr int KR = TK > 0 && TK <= kBwdRegTK ? TK : 1;
+#pragma unroll
+      for (int k = 0; k < kBwdRegPos; ++k) {
+        if (pos_dst[k] >= 0) {
+          const uint32_t l = pos_lut[k];
+          const int n_halo = (int)((l >> 16) & 15u), o0 = (int)(l >> 20);
+          const float* sp0 = in_s + (l & 0xffffu);
+          const float* sp1 = in_s + ent[n_halo ? o0 : 0];           // first halo copy (most border positions have one)
+          float acc[KR];
+#pragma unroll
+          for (int j = 0; j < KR; ++j) {
+            acc[j] = sp0[j * HoWo];
+            const float v = sp1[j * HoWo];
+            if (n_halo) acc[j] += v;
+          }
+          if (n_halo > 1) {
+#pragma unroll 1
+            for (int o = o0 + 1; o < o0 + n_halo; ++o) {
+              const float* sp = in_s + ent[o];
+#pragma unroll
+              for (int j = 0; j < KR; ++j) acc[j] += sp[j * HoWo];
+            }
+          }
+          float* __restrict__ dp = out + pos_dst[k];
+#pragma unroll
+          for (int j = 0; j < KR; ++j) __stcs(dp + j * HW, acc[j]);
+        }
+      }
+    } else if (TK > 0 && kl == TK) {
       constexpr int KB = TK >= 8 ? 8 : (TK > 0 ? TK : 1);
 #pragma unroll 1
       for (int e = ctid; e < n_in; e += n_cons) {

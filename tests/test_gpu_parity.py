@@ -688,6 +688,26 @@ def test_c2e_backward_matches_autograd(dev):
         torch.testing.assert_close(x.grad.double(), want, rtol=0, atol=1e-4)
 
 
+@pytest.mark.parametrize("align", [False, True])
+@pytest.mark.parametrize("w,C,B", [(2, 17, 3), (3, 5, 2), (7, 37, 3), (8, 1000, 5), (8, 16, 300), (14, 21, 2), (16, 70, 3)])
+def test_c2e_backward_team_split(dev, w, C, B, align):
+    """The shared-memory backward splits cube pixels with many contributors (pole pixels: 46 at w = 8, 90 at w = 16) over lane
+    teams: every batch / channel-group remainder / face width against a float64 gather over the transposed plan, twice
+    (bit-reproducible)."""
+    c2e = cp360_b200.Cube2Equi(w, align_corners=align)
+    g = torch.randn(B, C, 2 * w, 4 * w, device=dev)
+    got = c2e._backward(g)
+    assert torch.equal(got, c2e._backward(g))
+    offs, pix, wts = (t.cpu().numpy() for t in c2e._bwd_plan_on(g.device))
+    n = int(offs[-1])
+    owner = np.repeat(np.arange(6 * w * w), np.diff(offs))
+    contrib = g.reshape(B * C, -1).double()[:, torch.from_numpy(pix[:n].astype(np.int64)).to(dev)] * torch.from_numpy(wts[:n]).to(dev).double()
+    want = torch.zeros(B * C, 6 * w * w, device=dev, dtype=torch.float64)
+    want.index_add_(1, torch.from_numpy(owner).to(dev), contrib)
+    want = want.reshape(B, C, 6, w * w).permute(0, 2, 1, 3).reshape(6 * B, C, w, w)
+    torch.testing.assert_close(got.double(), want, rtol=0, atol=2e-5 * max(1, int(np.diff(offs).max()) // 8))
+
+
 @pytest.mark.parametrize("w,C,B", [(7, 1000, 1), (8, 2048, 2), (8, 5, 3), (16, 64, 2), (20, 7, 2), (40, 3, 1)])
 def test_c2e_max_with_indices_and_backward(dev, w, C, B):
     """Differentiable fused c2e + channel max (train_temporal.py:105-107): value and arg-max channel equal

@@ -84,6 +84,22 @@ def main():
             same = float((mx - full.max(1)[0]).abs().max()) == 0.0
             ok &= same
             print("%-58s %s" % ("c2e max == max(c2e) [%d,%d,%d,%d]" % (6 * B, C, w, w), "bit-exact" if same else "MISMATCH"), flush=True)
+    if "c2ebwd" in only or "c2e" in only:
+        # shared-memory backward: two-stage ring re-used every second channel group (B = 40: each CTA walks ~9-20 groups)
+        for w, C, B in [(8, 1000, 40), (16, 300, 30)]:
+            c2e = cp360_b200.Cube2Equi(w)
+            gy = torch.randn((B, C, 2 * w, 4 * w), device=dev, generator=g)
+            x = torch.zeros((6 * B, C, w, w), device=dev, requires_grad=True)
+            c2e.to_equi_nn(x).backward(gy)                       # same plan, but x.grad from our kernel
+            got = c2e._backward(gy)
+            os.environ["CP360_C2E_BWD_SMALL"] = "0"
+            want = c2e._backward(gy)
+            del os.environ["CP360_C2E_BWD_SMALL"]
+            diff = float((got - want).abs().max())
+            good = diff <= 1e-4 and torch.equal(got, x.grad)
+            ok &= good
+            print("%-58s %s (max diff vs read-only-path gather %.2e)" % ("c2e bwd [%d,%d,%d,%d]" % (B, C, 2 * w, 4 * w),
+                                                                        "ok" if good else "MISMATCH", diff), flush=True)
     if "e2c" in only:
         rng = np.random.default_rng(0)
         H, W, w, B = 240, 480, 64, 5
