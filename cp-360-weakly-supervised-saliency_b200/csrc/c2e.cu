@@ -605,9 +605,15 @@ c2e_bwd_gather_kernel(const float* __restrict__ gequi, const int32_t* __restrict
 // backward of the fused channel max, single-owner form: a thread owns one cube pixel of one frame and adds the
 // routed gradients of its contributors (gsal[b,p] * weight into channel argmax[b,p]) one after the other — no two
 // threads ever write the same element, so no atomics and a fixed summation order. gcube is zero-filled first.
+// A pole pixel has 46 (w = 8) .. 90 (w = 16) contributors: one dependent read-modify-write per contributor would be
+// a chain of that many memory round trips, so the contributors are taken eight at a time — their routing loads and
+// the eight current values are independent loads, the in-order additions (a later contributor of the same channel
+// continues from the earlier one's sum) happen in registers, then the eight stores go out in order.
+constexpr int kMaxBwdBatch = 8;
+
 __global__ void __launch_bounds__(kC2eThreads)
 c2e_max_bwd_gather_kernel(const float* __restrict__ gsal, const int32_t* __restrict__ arg, const int32_t* __restrict__ offs,
-                          const int32_t* __restrict__ pix, const float* __restrict__ wts, float* __restrict__ gcube,
+                          const int32_t* __restrict__ pix, const float* __restrict__ wts, float* gcube,
                           int64_t B, int C, int w) {
   const int ww = w * w, P = 8 * ww, NC = 6 * ww;
   const int cell = blockIdx.x * kC2eThreads + threadIdx.x;
@@ -616,11 +622,35 @@ c2e_max_bwd_gather_kernel(const float* __restrict__ gsal, const int32_t* __restr
   const int f = cell / ww, r = cell - f * ww;
   for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
     float* base = gcube + ((b * 6 + f) * C) * (int64_t)ww + r;
-    for (int e = e0; e < e1; ++e) {
-      const int p = __ldg(pix + e);
-      const int c = __ldg(arg + b * (int64_t)P + p);
-      if ((unsigned)c >= (unsigned)C) continue;          // never produced by the forward; guards foreign input
-      base[(int64_t)c * ww] += __ldg(gsal + b * (int64_t)P + p) * __ldg(wts + e);
+    for (int e = e0; e < e1; e += kMaxBwdBatch) {
+      int ch[kMaxBwdBatch];
+      float val[kMaxBwdBatch], cur[kMaxBwdBatch];
+#pragma unroll
+      for (int i = 0; i < kMaxBwdBatch; ++i) {
+        ch[i] = -1;
+        val[i] = 0.0f;
+        if (e + i < e1) {
+          const int p = __ldg(pix + e + i);
+          const int c = __ldg(arg + b * (int64_t)P + p);
+          if ((unsigned)c < (unsigned)C) {               // anything else is never produced by the forward; guards foreign input
+            ch[i] = c;
+            val[i] = __ldg(gsal + b * (int64_t)P + p) * __ldg(wts + e + i);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxBwdBatch; ++i) cur[i] = ch[i] >= 0 ? base[(int64_t)ch[i] * ww] : 0.0f;
+#pragma unroll
+      for (int i = 0; i < kMaxBwdBatch; ++i) {
+        float acc = cur[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j)
+          if (ch[j] == ch[i]) acc = cur[j];              // the latest earlier contributor of this channel
+        cur[i] = acc + val[i];
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxBwdBatch; ++i)
+        if (ch[i] >= 0) base[(int64_t)ch[i] * ww] = cur[i];
     }
   }
 }
