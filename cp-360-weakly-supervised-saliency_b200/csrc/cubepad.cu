@@ -20,6 +20,7 @@
 // for the host-side index map exported to the parity tests.
 #include <algorithm>
 #include <cmath>
+#include <array>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -663,6 +664,8 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
   a->ring_off = (a->ent_off + 6 * (HoWo - HW) * 2 + 127) & ~127;
   a->d_HW = make_fastdiv((uint32_t)HW);
   a->reg_pos = env_int("CP360_BWD_REG_POS", 1);
+  a->tab = nullptr; a->tab_out = nullptr;
+  a->tab_words = (a->ring_off - a->lut_off) / 4;
   size_t smem = (size_t)a->ring_off + (size_t)stages * a->stage_words * 4;
   while (smem > 220 * 1024 && stages > 2) {
     --stages;
@@ -672,6 +675,39 @@ static bool cube_bwd_plan(const CubePadGeom& g, int64_t n_faces, int C, const vo
   a->stages = stages;
   *smem_out = smem;
   return true;
+}
+
+// The position tables of the backward cube-tile kernel depend only on (geometry, kmax): built once per device by a
+// one-CTA launch of the kernel itself and kept in device memory (a few KB per geometry, never freed), so that every
+// later launch starts with one bulk copy instead of ~15 us of plate walks per CTA. The first use of a geometry
+// synchronises the stream once; inside a stream capture an unseen geometry falls back to building in every CTA.
+static std::mutex g_bwd_tab_mutex;
+static std::map<std::array<int, 8>, uint32_t*> g_bwd_tabs;
+
+static const uint32_t* bwd_table(void (*kern)(const CubeBwdArgs, const CubePadGeom), const CubeBwdArgs& a, size_t smem,
+                                 const CubePadGeom& g, unsigned threads, cudaStream_t st) {
+  if (!env_int("CP360_BWD_TABLE_CACHE", 1)) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  const std::array<int, 8> key = {dev, g.H, g.W, g.pl, g.pr, g.pt, g.pd, a.kmax};
+  std::lock_guard<std::mutex> lock(g_bwd_tab_mutex);
+  auto it = g_bwd_tabs.find(key);
+  if (it != g_bwd_tabs.end()) return it->second;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+  const size_t bytes = 16 + (size_t)a.tab_words * 4 + (((size_t)6 * g.H * g.W * 2 + 15) & ~(size_t)15);
+  uint32_t* d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  CubeBwdArgs b = a;
+  b.tab = nullptr; b.tab_out = d; b.work = nullptr; b.n_chunks = 0;
+  launch_kernel(kern, 1u, threads, smem, st, b, g);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(d);
+    return nullptr;
+  }
+  g_bwd_tabs[key] = d;
+  return d;
 }
 
 static int launch_cube_bwd(CubeBwdArgs a, size_t smem, const CubePadGeom& g, cudaStream_t st) {
@@ -688,6 +724,7 @@ static int launch_cube_bwd(CubeBwdArgs a, size_t smem, const CubePadGeom& g, cud
   }
   CP360_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cons_warps = std::min(kCubeMaxConsWarps, std::max(1, env_int("CP360_BWD_WARPS", 16)));
+  a.tab = bwd_table(kern, a, smem, g, 32u * (cons_warps + 1), st);
   a.work = acquire_work_counter(st);
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((a.n_chunks + 1) / 2, (int64_t)sm_count()));
   launch_kernel(kern, (unsigned)grid, 32 * (cons_warps + 1), smem, st, a, g);

@@ -39,6 +39,12 @@ struct CubeBwdArgs {
   int32_t ring_off;     // byte offset of the staging ring
   FastDiv d_HW;         // e / (H*W)
   int32_t reg_pos;      // 0: never use the register-cached position walk (A/B)
+  // position tables prebuilt in global memory (a pure function of the geometry and kmax; cached per device by the
+  // launcher): {n_interior, n_border, 0, 0} | tab_words words = the shared-memory image [lut_off, ring_off) |
+  // uint16 [6*H*W] positions, interior ones first. tab == nullptr: every CTA builds them itself.
+  const uint32_t* tab;
+  uint32_t* tab_out;    // != nullptr: this launch (one CTA) only builds the tables and writes them here
+  int32_t tab_words;
 };
 
 constexpr int kBwdRegPos = 12;   // positions per consumer thread that the register-cached walk holds (6*32*32 / 512)
@@ -62,6 +68,8 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
   const int kmax = TK ? TK : a.kmax;
   const int fstride = kmax * HoWo;                                        // face stride in a stage
   const int pm = max(max(g.pl, g.pr), max(g.pt, g.pd));
+  const bool have_tab = a.tab != nullptr, builder = a.tab_out != nullptr;
+  uint64_t* tabbar = reinterpret_cast<uint64_t*>(chunk_of + kCubeMaxStages) + 1;   // after the two list counters
 
   pdl_trigger();
   // ---- producer state (thread 0). Dynamic dealing: the first chunk of a CTA is its own index (no round trip to the
@@ -110,19 +118,36 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
       tma::mbar_init(&empty[s], n_cons);
 #endif
     }
+    tma::mbar_init(tabbar, 1);
     tma::fence_mbar_init();
-    // the first stages - 1 chunks stream in while the tables below are built; the last stage is their scratch
-    pdl_wait();
-    for (int i = 0; i + 1 < a.stages && !pdone; ++i) produce();
+    if (have_tab) {
+      tma::mbar_expect_tx(tabbar, (uint32_t)a.tab_words * 4u);
+      tma::bulk_load(smem_raw + a.lut_off, a.tab + 4, (uint32_t)a.tab_words * 4u, tabbar);
+    }
+    if (!builder && !have_tab) {
+      // the first stages - 1 chunks stream in while the tables below are built; the last stage is their scratch
+      pdl_wait();
+      for (int i = 0; i + 1 < a.stages && !pdone; ++i) produce();
+    }
   }
   __syncwarp();
   // ---- tables. Only pixels within a pad width of a face edge receive halo copies (at H = 32: 12 % of the positions,
   // two lanes of every warp of a raster walk): they are first compacted into a list (in the idle last stage), so the
   // plate walks below run on full warps.
+  // The register-cached walk (2-channel stages) also takes the positions without copies as a list: its warps then
+  // hold either only such positions (two loads, two stores each) or border positions.
   uint16_t* blist = reinterpret_cast<uint16_t*>(const_cast<float*>(ring) + (size_t)(a.stages - 1) * a.stage_words);
+  uint16_t* ilist = blist + n_in;                      // 4 B * n_in of scratch <= one stage (6 * kmax * Ho * Wo floats)
   int* n_border = reinterpret_cast<int*>(chunk_of + kCubeMaxStages);
-  if (tid == 0) *n_border = 0;
+  int* n_interior = n_border + 1;
+  const int ctid = tid - 32;
+  const int64_t CHW = (int64_t)a.C * HW;
+  const bool reg_cached = TK > 0 && TK <= kBwdRegTK && n_in <= kBwdRegPos * n_cons && a.reg_pos != 0;
+  if (tid == 0) { *n_border = 0; *n_interior = 0; }
   __syncthreads();
+  if (have_tab) {
+    if (warp != 0) tma::mbar_wait(tabbar, 0);          // the producer warp goes straight to its loads
+  } else {
   for (int e0 = warp * 32; e0 < n_in; e0 += (int)blockDim.x) {
     const int e = e0 + lane;
     bool border = false;
@@ -137,6 +162,13 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     if (lane == 0 && m) base = atomicAdd(n_border, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (border) blist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)e;
+    if (reg_cached || builder) {                       // a warp's run of interior pixels stays contiguous: coalesced stores
+      const unsigned mi = __ballot_sync(0xffffffffu, e < n_in && !border);
+      int ibase = 0;
+      if (lane == 0 && mi) ibase = atomicAdd(n_interior, __popc(mi));
+      ibase = __shfl_sync(0xffffffffu, ibase, 0);
+      if (e < n_in && !border) ilist[ibase + __popc(mi & ((1u << lane) - 1u))] = (uint16_t)e;
+    }
   }
   __syncthreads();
   const int nb = *n_border;
@@ -150,11 +182,11 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     lut[e] = (uint32_t)cnt;
   }
   __syncthreads();
-  if (warp == 0) {                                     // exclusive scan in place, one contiguous segment per lane
-    const int seg = (n_in + 31) / 32;
-    const int b = min(lane * seg, n_in), e1 = min(b + seg, n_in);
+  if (warp == 0) {                                     // exclusive scan over the border list, one contiguous segment per lane
+    const int seg = (nb + 31) / 32;
+    const int b = min(lane * seg, nb), e1 = min(b + seg, nb);
     int sum = 0;
-    for (int i = b; i < e1; ++i) sum += (int)lut[i];
+    for (int i = b; i < e1; ++i) sum += (int)lut[blist[i]];
     int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -163,8 +195,9 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     }
     int run = incl - sum;
     for (int i = b; i < e1; ++i) {
-      const int c = (int)lut[i];
-      lut[i] = (uint32_t)run | (uint32_t)c << 16;      // start | count (start < 4096, count < 16: checked on the host)
+      const int e = blist[i];
+      const int c = (int)lut[e];
+      lut[e] = (uint32_t)run | (uint32_t)c << 16;      // start | count (start < 4096, count < 16: checked on the host)
       run += c;
     }
   }
@@ -188,7 +221,40 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     const uint32_t inner = (uint32_t)(f * fstride + (y + g.pt) * g.Wo + x + g.pl);
     lut[e] = inner | (uint32_t)cnt << 16 | (uint32_t)start << 20;
   }
-  __syncthreads();                                     // also: every read of the scratch list is done before stage stages-1 is loaded
+  __syncthreads();
+  }  // !have_tab
+  if (builder) {                                       // hand the tables to the launcher's cache
+    const int n_int = *n_interior, nbb = *n_border;
+    if (tid == 0) { a.tab_out[0] = (uint32_t)n_int; a.tab_out[1] = (uint32_t)nbb; a.tab_out[2] = 0; a.tab_out[3] = 0; }
+    const uint32_t* img = reinterpret_cast<const uint32_t*>(smem_raw + a.lut_off);
+    for (int i = tid; i < a.tab_words; i += blockDim.x) a.tab_out[4 + i] = img[i];
+    uint16_t* ol = reinterpret_cast<uint16_t*>(a.tab_out + 4 + a.tab_words);
+    for (int i = tid; i < n_in; i += blockDim.x) ol[i] = i < n_int ? ilist[i] : blist[i - n_int];
+    return;
+  }
+  // register-cached walk: slot i = ctid + k * n_cons of [interior list | border list]; bit k of no_halo: every lane of
+  // this warp holds an interior position there
+  uint32_t pos_lut[kBwdRegPos];
+  int pos_dst[kBwdRegPos];                              // destination offset inside the cube's block (< 2^31: host check), -1: none
+  unsigned no_halo = 0;
+  if (TK > 0 && TK <= kBwdRegTK && warp != 0) {
+    const int n_int = have_tab ? (int)__ldg(a.tab) : *n_interior;
+    const uint16_t* olist = reinterpret_cast<const uint16_t*>(a.tab + 4 + a.tab_words);
+#pragma unroll
+    for (int k = 0; k < kBwdRegPos; ++k) {
+      const int i = ctid + k * n_cons;
+      pos_lut[k] = 0;
+      pos_dst[k] = -1;
+      if (reg_cached && ctid >= 0 && i < n_in) {
+        const int e = have_tab ? (int)__ldg(olist + i) : (i < n_int ? ilist[i] : blist[i - n_int]);
+        const int f = fdiv(e, a.d_HW);
+        pos_lut[k] = lut[e];
+        pos_dst[k] = f * (int)CHW + (e - f * HW);
+      }
+      if (__all_sync(0xffffffffu, reg_cached && ctid >= 0 && i < n_int)) no_halo |= 1u << k;
+    }
+  }
+  if (!have_tab) __syncthreads();                      // every read of the scratch lists is done before stage stages-1 is loaded
   pdl_wait();
 
   if (warp == 0) {
@@ -204,24 +270,6 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
     return;
   }
   // ---------------- consumers
-  const int ctid = tid - 32;
-  const int64_t CHW = (int64_t)a.C * HW;
-  const bool reg_cached = TK > 0 && TK <= kBwdRegTK && n_in <= kBwdRegPos * n_cons && a.reg_pos != 0;
-  uint32_t pos_lut[kBwdRegPos];
-  int pos_dst[kBwdRegPos];                              // destination offset inside the cube's block (< 2^31: host check), -1: none
-  if (TK > 0 && TK <= kBwdRegTK) {
-#pragma unroll
-    for (int k = 0; k < kBwdRegPos; ++k) {
-      const int e = ctid + k * n_cons;
-      pos_lut[k] = 0;
-      pos_dst[k] = -1;
-      if (reg_cached && e < n_in) {
-        const int f = fdiv(e, a.d_HW);
-        pos_lut[k] = lut[e];
-        pos_dst[k] = f * (int)CHW + (e - f * HW);
-      }
-    }
-  }
   int s = 0;
   uint32_t ph = 0;
   while (true) {
@@ -237,9 +285,22 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
       // few channels per stage (32x32 faces: 2): the per-position words above cost more than the data moves,
       // so they live in registers across chunks (every thread owns the same positions in every chunk)
       constexpr int KR = TK > 0 && TK <= kBwdRegTK ? TK : 1;
+      float* outj[KR];                                 // one materialised base pointer per channel plane: a store is then
+#pragma unroll                                         // one IMAD.WIDE + STG instead of a re-derived 64-bit index
+      for (int j = 0; j < KR; ++j) {
+        outj[j] = out + j * HW;
+        asm volatile("" : "+l"(outj[j]));
+      }
 #pragma unroll
       for (int k = 0; k < kBwdRegPos; ++k) {
-        if (pos_dst[k] >= 0) {
+        if (no_halo >> k & 1u) {                       // warp-uniform
+          const float* sp0 = in_s + (pos_lut[k] & 0xffffu);   // no copies to add
+          float acc[KR];
+#pragma unroll
+          for (int j = 0; j < KR; ++j) acc[j] = sp0[j * HoWo];
+#pragma unroll
+          for (int j = 0; j < KR; ++j) __stcs(outj[j] + pos_dst[k], acc[j]);
+        } else if (pos_dst[k] >= 0) {
           const uint32_t l = pos_lut[k];
           const int n_halo = (int)((l >> 16) & 15u), o0 = (int)(l >> 20);
           const float* sp0 = in_s + (l & 0xffffu);
@@ -259,9 +320,8 @@ cubepad_bwd_cube_kernel(const CubeBwdArgs a, const __grid_constant__ CubePadGeom
               for (int j = 0; j < KR; ++j) acc[j] += sp[j * HoWo];
             }
           }
-          float* __restrict__ dp = out + pos_dst[k];
 #pragma unroll
-          for (int j = 0; j < KR; ++j) __stcs(dp + j * HW, acc[j]);
+          for (int j = 0; j < KR; ++j) __stcs(outj[j] + pos_dst[k], acc[j]);
         }
       }
     } else if (TK > 0 && kl == TK) {
