@@ -277,6 +277,32 @@ def test_cubepad_errors_and_edge_cases(dev):
     assert torch.equal(cp360_b200.CubePad(1)(x), gather_reference(x, ocp.index_map(8, 8, 1)))
 
 
+def test_cubepad_backward_table_cache_and_graph_capture(dev, monkeypatch):
+    """The backward cube-tile kernel takes its position tables from a per-geometry device cache (built by a one-CTA launch
+    at first use). Same bits with the cache off; a geometry first seen INSIDE a stream capture builds its tables in every
+    CTA instead (no allocation / synchronisation while capturing) and the replayed graph gives the same gradient."""
+    pads = (2, 1, 1, 2)
+    for shape in [(12, 6, 32, 32), (12, 64, 11, 11)]:
+        gy = torch.randn(shape[0], shape[1], shape[2] + pads[2] + pads[3], shape[3] + pads[0] + pads[1], device=dev)
+        monkeypatch.setenv("CP360_BWD_TABLE_CACHE", "0")
+        want = cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:])
+        monkeypatch.delenv("CP360_BWD_TABLE_CACHE")
+        gx = torch.empty_like(want)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):                   # geometry not cached yet
+                gx.copy_(cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:]))
+        gx.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(gx, want)
+        first = cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:])  # builds + caches the tables
+        again = cp360_b200.cube_pad.cubepad_backward(gy, pads, shape[2:])  # served from the cache
+        assert torch.equal(first, want) and torch.equal(again, want)
+
+
 def test_cubepad_backward_matches_autograd(dev):
     """Backward = transpose of the gather (train_temporal.py:167-170 back-propagates through it)."""
     for shape, pad in [((6, 3, 7, 7), 1), ((12, 4, 8, 8), [2, 1, 1, 3]), ((6, 2, 32, 32), 3), ((6, 5, 9, 9), [4, 2, 3, 5]),
