@@ -839,6 +839,8 @@ static int launch_row(const void* x, void* y, int64_t n_planes, int C, const Cub
   a.ring_off = (int)((kRowBarBytes + 6 * a.nb * 16 + align - 1) / align * align) + env_int("CP360_ROW_SMEM_PAD", 0);
   const int slot_align = std::max(32, env_int("CP360_ROW_SLOT_ALIGN_WORDS", 32));
   a.slot_words = (a.slot_words + slot_align - 1) / slot_align * slot_align;
+  if (kRowWarps != 8)                                          // experiment builds (-DCP360_ROW_WARPS): the table's ring depths assume 8 rings
+    while (a.slots > 2 && (size_t)a.ring_off + (size_t)kRowWarps * a.slots * a.slot_words * 4 > 220 * 1024) --a.slots;
   const size_t smem = (size_t)a.ring_off + (size_t)kRowWarps * a.slots * a.slot_words * 4;
   CP360_CHECK_ARG(smem <= 220 * 1024, CP360_ERR_SHAPE, "row kernel tile too large");
   bool epi = false;

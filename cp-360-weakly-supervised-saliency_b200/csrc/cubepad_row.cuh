@@ -45,7 +45,10 @@ __device__ __forceinline__ uint32_t epi_apply(uint32_t v, const Epi& e) {
   return __float_as_uint(f);
 }
 
-constexpr int kRowWarps = 8;
+#ifndef CP360_ROW_WARPS
+#define CP360_ROW_WARPS 8                              // measured on B200: 12 / 16 warps per CTA (smaller rings each) are slower — profiles/README.md
+#endif
+constexpr int kRowWarps = CP360_ROW_WARPS;
 constexpr int kRowThreads = kRowWarps * 32;
 constexpr int kRowMaxSlots = 8;
 constexpr int kRowMetaOff = kRowWarps * kRowMaxSlots * 8;            // per-slot (plane, band) of the tile in flight
@@ -260,12 +263,12 @@ cubepad_row_kernel(const RowArgs a, const __grid_constant__ CubePadGeom g) {
       u_next = gl + 2;
     } else if (a.order == 2) {
       const int k = atomicAdd(ctr, 1);
-      u = (k >> 3) * GW + blockIdx.x * kRowWarps + (k & 7);
+      u = (k / kRowWarps) * GW + blockIdx.x * kRowWarps + (k % kRowWarps);
     } else if (a.order == 5) {
       u = a.n_units;
       if (!u_left) {                                   // u_left doubles as "this warp is in the tail"
         const int k = atomicAdd(ctr, 1);
-        u = (k >> 3) * GW + blockIdx.x * kRowWarps + (k & 7);
+        u = (k / kRowWarps) * GW + blockIdx.x * kRowWarps + (k % kRowWarps);
         if (u >= a.n_static) u_left = 1;
       }
       if (u_left) u = a.n_static + (int)min(atomicAdd(a.work, 1u), (uint32_t)(a.n_units - a.n_static));
