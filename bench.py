@@ -597,6 +597,11 @@ def run_chain(args, ctx):
     if os.environ.get("CP360_BENCH_SITES"):
         for k, v in sites_tbl.items():
             print("site %-34s %8.1f us %8.1f GB/s %.2f (x%d)" % (k, v["us"], v["gbs"], v["frac"], v["launches_per_step"]), file=sys.stderr)
+        if os.environ.get("CP360_BENCH_SITES") == "2":          # where the allocator put each site's tensors (placement experiments)
+            for i, (C, H, p) in enumerate(pipe.sites):
+                a, b = pipe.site_in[i].data_ptr(), pipe.site_out[i].data_ptr()
+                print("ptrs site %d %dx%d in %#x out %#x  in%%2M %7d KB out%%2M %7d KB  (out-in)%%2M %7d KB" % (
+                    i, C, H, a, b, (a >> 10) % 2048, (b >> 10) % 2048, ((b - a) >> 10) % 2048), file=sys.stderr)
     chain_gbs = pipe.bytes_per_frame() * B * K / (ms * 1e-3) / 1e9
     roofline, dom = roofline_from(per_class, peak, peak_src,
                                   {"chain_gbs": round(chain_gbs / world, 1), "chain_frac": round(chain_gbs / world / peak, 4)})
