@@ -138,8 +138,14 @@ CP360_API int cp360_cubepad_build_inverse_map(int H, int W, int pl, int pr, int 
 /* Device, fp32: gx[6N,C,H,W] = dCubePad^T(gy[6N,C,Ho,Wo]) — every input pixel receives the sum
  * of the gradients of all output pixels that copied it (what autograd derives from the
  * cat/index_select/repeat chain; needed by temporal_model/train_temporal.py:167-170). No atomics
- * (a copy kernel for the face interiors, a gather kernel for the pixels halo positions copy): the sum runs in the fixed order of cp360_cubepad_build_inverse_map, so gradients are
- * reproducible bit for bit. */
+ * (faces up to 32 px: one pass over the staged padded gradient of a whole cube; larger faces: a copy
+ * kernel for the face interiors and a gather kernel for the pixels that halo positions copy): the sum
+ * runs in the fixed order of cp360_cubepad_build_inverse_map, so gradients are reproducible bit for bit.
+ * The small-face kernel keeps its position tables (a few KB, a pure function of H, W and the pads) in a
+ * per-device cache: the FIRST call for a geometry allocates them, builds them with a one-CTA launch on
+ * `stream` and synchronises that stream once; later calls do neither. A geometry first seen while
+ * `stream` is being captured builds the tables inside every CTA instead (no allocation, no
+ * synchronisation during capture). CP360_BWD_TABLE_CACHE=0 disables the cache. */
 CP360_API int cp360_cubepad_bwd_f32(const float* gy_dev, float* gx_dev, int64_t n_faces, int64_t C, int H,
                           int W, int pl, int pr, int pt, int pd, void* stream);
 
