@@ -152,17 +152,24 @@ __device__ __forceinline__ void row_copy(const uint32_t* __restrict__ sp, uint32
     // wide rows: one row per step, NJ loads in flight — two rows per step when an epilogue sits between the
     // load and the store (its dependent ALU chain needs more independent work to hide behind)
     int r = 0;
-    if (EPI && NJc <= 4) {
+#ifndef CP360_ROW_EPI_ROWS
+#define CP360_ROW_EPI_ROWS 2
+#endif
+#ifndef CP360_ROW_WIDE_ROWS
+#define CP360_ROW_WIDE_ROWS 1
+#endif
+    if ((EPI && NJc <= 4) || (!EPI && NJc <= 4 && CP360_ROW_WIDE_ROWS > 1)) {
+      constexpr int KR = EPI ? CP360_ROW_EPI_ROWS : CP360_ROW_WIDE_ROWS;
 #pragma unroll 1
-      for (; r + 2 <= nr; r += 2, sp += 2 * W, dp += 2 * Wo) {
-        uint32_t v[2][NJc];
+      for (; r + KR <= nr; r += KR, sp += KR * W, dp += KR * Wo) {
+        uint32_t v[KR][NJc];
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < KR; ++k)
 #pragma unroll
           for (int j = 0; j < NJc; ++j)
             if (j < NJc - 1 || tail_ok) v[k][j] = sp[k * W + j * 32];
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < KR; ++k)
 #pragma unroll
           for (int j = 0; j < NJc; ++j)
             if (j < NJc - 1 || tail_ok) CP360_ROW_ST(dp + k * Wo + j * 32, epi_apply<EPI>(v[k][j], ep));
