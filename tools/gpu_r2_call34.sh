@@ -4,7 +4,7 @@ TAG=${1:-r2c34}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 L=$PWD/cp-360-weakly-supervised-saliency_b200/lib
-for v in product epi3 epi4 wide2 product; do
+for v in ${VARIANTS:-product epi3 epi4 wide2 product}; do
   if [ $v = product ]; then unset CP360_LIB; else export CP360_LIB=$L/libcp360_$v.so; fi
   CP360_BENCH_SITES=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-e2e --no-aten-baseline > $OUT/bench_$v.json 2> $OUT/bench_$v.err
   python - <<PY
