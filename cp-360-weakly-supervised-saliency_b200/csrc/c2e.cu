@@ -271,8 +271,8 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
     for (int f = 0; f < 6; ++f)
       tma::bulk_load(dst + (size_t)f * fstride + kFaceSkew[f], a.cube + (((int64_t)b * 6 + f) * a.C + c0) * ww, bytes, &full[s]);
   };
-  if (tid < 32) {                                        // warp-uniform branch, predicated body: warp 0 never diverges here
-    if (tid < a.stages) tma::mbar_init(&full[tid], 1);
+  if (tid < 32) {                                        // warp-uniform branch, predicated instruction: warp 0 never diverges here
+    tma::mbar_init_if(tid < a.stages, &full[tid < a.stages ? tid : 0], 1);
     tma::fence_mbar_init();
   }
   __syncthreads();

@@ -19,6 +19,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
                : "memory");
 }
 
+// Predicated form: every lane executes the instruction, only lanes with `on` initialise — no branch, so the warp
+// cannot be lane-divergent at a following barrier (compute-sanitizer synccheck, profiles/README.md).
+__device__ __forceinline__ void mbar_init_if(bool on, uint64_t* bar, uint32_t arrivals) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p mbarrier.init.shared::cta.b64 [%0], %1;\n\t}"
+               ::"r"(smem_addr(bar)), "r"(arrivals), "r"((uint32_t)on)
+               : "memory");
+}
+
 // Make barrier initialisation visible to the async proxy before the first bulk copy.
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
