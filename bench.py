@@ -49,6 +49,8 @@ def workload_string(args):
     chain = ("chain per frame: e2c 960x1920x3 -> 6x3x%dx%d; CubePad at the 18 cubic-ResNet-50 sites "
              "(cube %d) + [6,%d,%d,%d] p1; c2e+channel-max [6,%d,%d,%d] -> [%d,%d]; fp32"
              % (args.cube, args.cube, args.cube, FEAT_C, fw, fw, CAM_C, fw, fw, 2 * fw, 4 * fw))
+    if args.workload in ("chain", "corpus") and not getattr(args, "no_fuse_first_site", False):
+        chain += "; e2c and the CubePad(3) in front of conv1 run as one kernel (same padded tensor, the unpadded faces are not materialised)"
     if args.workload == "chain":
         return chain
     if args.workload == "corpus":
@@ -83,6 +85,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aten-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true")
+    ap.add_argument("--no-fuse-first-site", action="store_true",
+                    help="chain / corpus: run e2c and the CubePad(3) in front of conv1 as two launches (the unpadded faces "
+                         "are written and read back) instead of the one-kernel first site (cp360_e2c_cubepad_fwd)")
     ap.add_argument("--host-alloc", default="torch_pin", choices=["torch_pin", "pinned", "write_combined", "hugepage"],
                     help="how the e2e host frame buffers are page-locked (cp360_b200.pinned_empty modes)")
     ap.add_argument("--e2e-depth", type=int, default=3, help="device staging ring depth of process_host")
@@ -504,14 +509,16 @@ def kernels_table(per_class, prof_steps):
             for k, c in per_class.items()}
 
 
-def attach_traffic(roofline, dom, B, cube):
-    """ncu captures are per launch at a stated batch and face width: only valid for a run at that configuration."""
+def attach_traffic(roofline, dom, B, cube, fused_first=True):
+    """ncu captures are per launch at a stated batch and face width: only valid for a run at that configuration
+    (and, for a class average, at that composition of the class: with or without the stem site)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
             tj = json.load(f)
-        if int(tj.get("_frames_per_launch", 16)) == B and int(tj.get("_cube", 256)) == cube and tj.get(dom) is not None:
-            roofline["traffic"] = tj.get(dom)
+        key = dom if fused_first or (dom + "__first_site_unfused") not in tj else dom + "__first_site_unfused"
+        if int(tj.get("_frames_per_launch", 16)) == B and int(tj.get("_cube", 256)) == cube and tj.get(key) is not None:
+            roofline["traffic"] = tj.get(key)
             roofline["traffic_source"] = "profiles/traffic.json (%s)" % tj.get("_source", "ncu --set full, B=%d" % B)
     except Exception:
         pass
@@ -544,7 +551,8 @@ def run_chain(args, ctx):
     W, K = ctx.W, ctx.K
     B = max(1, args.batch or 32)
     cube = args.cube
-    pipe = cp360_b200.SphericalPipeline(EQUI_H, EQUI_W, cube, CAM_C, FEAT_C, device=dev, seed=1234 + rank)
+    pipe = cp360_b200.SphericalPipeline(EQUI_H, EQUI_W, cube, CAM_C, FEAT_C, device=dev, seed=1234 + rank,
+                                        fuse_first_site=not args.no_fuse_first_site)
     pipe.allocate(B)
     frames = pipe.synthetic_frames(B)
     lib = _lib.lib()
@@ -578,6 +586,8 @@ def run_chain(args, ctx):
             kname = cubepad_kernel_name(lib, 6 * B, C, H, p)
             nbytes = pipe.cubepad_bytes_per_frame(pipe.sites[site]) * B
             skey = "%s %dx%dx%d" % (kname.split("_kernel")[0], C, H, p)
+        elif name == "e2c" and pipe.fuse_first_site:
+            kname, nbytes, skey = "e2c_cubepad_kernel", pipe.e2c_cubepad_bytes_per_frame() * B, "e2c_cubepad"
         elif name == "e2c":
             kname, nbytes, skey = "e2c_kernel", pipe.e2c_bytes_per_frame() * B, "e2c"
         else:
@@ -605,7 +615,7 @@ def run_chain(args, ctx):
     chain_gbs = pipe.bytes_per_frame() * B * K / (ms * 1e-3) / 1e9
     roofline, dom = roofline_from(per_class, peak, peak_src,
                                   {"chain_gbs": round(chain_gbs / world, 1), "chain_frac": round(chain_gbs / world / peak, 4)})
-    attach_traffic(roofline, dom, B, cube)
+    attach_traffic(roofline, dom, B, cube, pipe.fuse_first_site)
     kernels = kernels_table(per_class, prof_steps)
 
     # ---- the fused chain (SURVEY.md §8 row f2 / north_star (b) "or fused into the producer"), beside the headline
@@ -872,7 +882,8 @@ def run_corpus(args, ctx):
     a, b = cp360_b200.shard_range(CORPUS_FRAMES, rank, world)
     n_local = b - a
     B = args.batch or max(d for d in range(1, 41) if n_local % d == 0)
-    pipe = cp360_b200.SphericalPipeline(EQUI_H, EQUI_W, args.cube, CAM_C, FEAT_C, device=dev, seed=1234)
+    pipe = cp360_b200.SphericalPipeline(EQUI_H, EQUI_W, args.cube, CAM_C, FEAT_C, device=dev, seed=1234,
+                                        fuse_first_site=not args.no_fuse_first_site)
     pipe.allocate(B)
     lib = _lib.lib()
     # the rank's share of the corpus, resident in HBM (44 GB of fp32 frames on one GPU, SURVEY.md §8d-5: frames are
@@ -922,6 +933,8 @@ def run_corpus(args, ctx):
         if name == "cubepad":
             C, H, p = pipe.sites[site]
             kname, nbytes = cubepad_kernel_name(lib, 6 * B, C, H, p), pipe.cubepad_bytes_per_frame(pipe.sites[site]) * B
+        elif name == "e2c" and pipe.fuse_first_site:
+            kname, nbytes = "e2c_cubepad_kernel", pipe.e2c_cubepad_bytes_per_frame() * B
         elif name == "e2c":
             kname, nbytes = "e2c_kernel", pipe.e2c_bytes_per_frame() * B
         else:
@@ -946,7 +959,7 @@ def run_corpus(args, ctx):
                            "sharding": "contiguous frame blocks over ranks (shard_range), no collective inside a pass",
                            "launch": "eager C-ABI launches",
                            "l2": "every pass streams %.1f GB of frames + %.1f GB of features per GPU" %
-                                 (n_local * EQUI_H * EQUI_W * 12 / 1e9, (pipe.bytes_per_frame() - pipe.e2c_bytes_per_frame()) * n_local / 1e9),
+                                 (n_local * EQUI_H * EQUI_W * 12 / 1e9, (pipe.bytes_per_frame() - (pipe.e2c_cubepad_bytes_per_frame() if pipe.fuse_first_site else pipe.e2c_bytes_per_frame())) * n_local / 1e9),
                            "algorithmic_bytes_per_frame": pipe.bytes_per_frame()},
                 "corpus_wall_ms": round(ms / K, 3), "gather_ms": None if gather_ms is None else round(gather_ms, 4),
                 "gather": None if gather_ms is None else "all_gather_into_tensor of [%d,%d,%d] fp32 maps (NCCL), timed on its own over 10 calls"

@@ -158,7 +158,16 @@ class SphericalPipeline:
         w = self.feat_w
         return 6 * self.cam_channels * w * w * 4 + 8 * w * w * 4
 
+    def e2c_cubepad_bytes_per_frame(self):
+        """Algorithmic bytes of the fused first site (cp360_e2c_cubepad_fwd): unique input pixels touched + the
+        padded conv1 input written; the unpadded faces are neither written nor read."""
+        w, p0 = self.cube, self.sites[0][2]
+        return self.e2c_bytes_per_frame() - 6 * w * w * 3 * 4 + 6 * 3 * (w + 2 * p0) ** 2 * 4
+
     def bytes_per_frame(self):
+        if self.fuse_first_site:
+            return (self.e2c_cubepad_bytes_per_frame() + sum(self.cubepad_bytes_per_frame(s) for s in self.sites[1:]) +
+                    self.c2e_max_bytes_per_frame())
         return (self.e2c_bytes_per_frame() + sum(self.cubepad_bytes_per_frame(s) for s in self.sites) +
                 self.c2e_max_bytes_per_frame())
 
@@ -220,7 +229,7 @@ class SphericalPipeline:
 
     # ---------------------------------------------------------------- the step
     def launches_per_step(self):
-        return 1 + len(self.sites) + 2 - int(self.fuse_first_site)   # e2c, CubePads, -inf fill + c2e_max
+        return 1 + len(self.sites) + 1 - int(self.fuse_first_site)   # e2c, CubePads, c2e + channel max (one cluster kernel)
 
     def step(self, frames, on_launch=None):
         """frames [B,Hin,Win,3] fp32 (or uint8) on self.device -> sal [B,2fw,4fw] (buffer reused each step).
@@ -270,7 +279,7 @@ class SphericalPipeline:
           cp360_cubepad_fused_fwd x 2      the ConvLSTM site as CubePad(cat(a, b)) written one source at a time
           cp360_c2e_max_fwd                back-projection + channel max
         Site outputs equal CubePad applied to the affine+ReLU'd / concatenated inputs bit for bit
-        (tests/test_gpu_parity.py::test_pipeline_fused_chain_matches_unfused_ops)."""
+        (tests/test_pipeline_gpu.py::test_step_fused_equals_pad_of_the_producer_ops)."""
         if frames.shape[0] != self.B:
             self.allocate(frames.shape[0])
         lib, chk = self._lib, _lib.check
