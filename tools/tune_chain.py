@@ -146,15 +146,19 @@ def main():
     ap.add_argument("--out", default="gpurun_out/tune")
     ap.add_argument("--frames", default="1,2,4,8,16,32,64")
     ap.add_argument("--passes", type=int, default=2)
+    ap.add_argument("--cubes", default="256,224")
+    ap.add_argument("--two-launch-first-site", action="store_true",
+                    help="tune inside the 21-launch chain (e2c, then the stem CubePad) instead of bench.py's default 20-launch one")
+    ap.add_argument("--skip-clstm", action="store_true")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     dev = torch.device("cuda", 0)
     lib = _lib.lib()
     table = read_table(args.base)
     log = []
-    for cube in (256, 224):
-        pipe = cp360_b200.SphericalPipeline(960, 1920, cube, 1000, 2048, device=dev)
-        sites = list(dict.fromkeys(pipe.sites))
+    for cube in [int(v) for v in args.cubes.split(",")]:
+        pipe = cp360_b200.SphericalPipeline(960, 1920, cube, 1000, 2048, device=dev, fuse_first_site=not args.two_launch_first_site)
+        sites = list(dict.fromkeys(pipe.sites if args.two_launch_first_site else pipe.sites[1:]))   # the fused stem is not a CubePad launch
         for B in [int(v) for v in args.frames.split(",")]:
             pipe.allocate(B)
             frames = pipe.synthetic_frames(B)
@@ -170,7 +174,7 @@ def main():
             del frames
         del pipe
         torch.cuda.empty_cache()
-    for (c, w) in ((2048, 8), (1000, 7)):
+    for (c, w) in (() if args.skip_clstm else ((2048, 8), (1000, 7))):
         for B in [int(v) for v in args.frames.split(",") if int(v) <= 32]:
             seq = cp360_b200.TemporalCubePadSequence(c, c, w, 5, device=dev, fused_cat=False)
             seq.allocate(B)
