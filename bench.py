@@ -9,7 +9,9 @@
 Workloads (BASELINE.json configs):
   chain   (default, the headline) one step = SphericalPipeline.step over B frames per GPU: e2c, the 18 cubic-ResNet-50
           CubePad sites, the 2048-channel CubePad site, c2e + channel max. --cube 224 is the reference's own
-          cube_dim (config.yaml:17); weak scaling, frames sharded over ranks.
+          cube_dim (config.yaml:17); weak scaling, frames sharded over ranks. e2c and the CubePad(3) in front of
+          conv1 run as ONE kernel (the same padded tensor; 20 launches per step) unless --no-fuse-first-site
+          (21 launches: the faces are written, then read by the stem pad — round 1's definition).
   clstm   configs[3]: one step = one 80-frame video through the ConvLSTM-side hot path: per output frame a 5-step
           window (test_temporal.py:57-79) of the three CubePads of a cell evaluation (clstm.py:57-64) + c2e + max
           of the hidden state; B windows batched per launch. --clstm-variant reference = 1000 channels on 7x7 faces.
