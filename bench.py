@@ -87,6 +87,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aten-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true")
+    ap.add_argument("--min-untimed-steps", type=int, default=40,
+                    help="at least this many untimed steps before a timed region (max with --warmup; 0 = exactly --warmup)")
     ap.add_argument("--no-fuse-first-site", action="store_true",
                     help="chain / corpus: run e2c and the CubePad(3) in front of conv1 as two launches (the unpadded faces "
                          "are written and read back) instead of the one-kernel first site (cp360_e2c_cubepad_fwd)")
@@ -397,6 +399,10 @@ class Ctx:
         if world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.W, self.K = max(3, args.warmup), max(1, args.steps)
+        # steady state: a run with few warm-up steps reads 2-3 % low (tools/gpu_r2_call41.sh: 20 steps after 3 warm-up steps
+        # 25.9-26.2 k frames/s, after 50: 27.0 k, 200 steps after 10: 26.5 k on the same box) — the first replays of a graph
+        # and the clock ramp out of idle. At least this many untimed steps precede every timed region (stated in `config`).
+        self.min_untimed = 0 if args.profile_range else max(0, args.min_untimed_steps)
         self.sampler = ClockSampler(self.dev)
 
     def barrier(self):
@@ -422,7 +428,7 @@ class Ctx:
         torch = self.torch
         K = self.K if steps is None else steps
         W = self.W if warmup is None else warmup
-        for _ in range(W):
+        for _ in range(max(W, self.min_untimed)):
             one_step()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -742,6 +748,7 @@ def run_chain(args, ctx):
                            "global_frames_per_step": world * B,
                            "sharding": "frames block-partitioned over ranks, no data-path collective",
                            "launch": "CUDA graph replay" if graph is not None else "eager C-ABI launches",
+                           "untimed_steps_before_timing": max(W, ctx.min_untimed),
                            "l2": "inputs larger than L2: %.2f GB touched per step per GPU, no flush needed"
                                  % (pipe.bytes_per_frame() * B / 1e9) if pipe.bytes_per_frame() * B > 300e6 else
                                  "%.0f MB touched per step per GPU: part of it stays in the 126 MB L2 between steps "
@@ -865,6 +872,7 @@ def run_clstm(args, ctx):
                            "frames_per_step_per_gpu": VIDEO_FRAMES, "seq_len": SEQ_LEN, "variant": args.clstm_variant,
                            "sharding": "videos over ranks (one video per rank per step), no data-path collective",
                            "launch": "CUDA graph replay" if graph is not None else "eager C-ABI launches",
+                           "untimed_steps_before_timing": max(W, ctx.min_untimed),
                            "l2": "%.2f GB touched per window batch, larger than L2" % (seq.bytes_per_frame() * B / 1e9),
                            "algorithmic_bytes_per_frame": seq.bytes_per_frame()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * K), "roofline": roofline,
