@@ -8,8 +8,11 @@
 // PADDED gradient is what is staged: six TMA bulk loads (one contiguous k*Ho*Wo chunk per face) per
 // tile, `stages` tiles ahead, every gy element read from DRAM exactly once, no atomics.
 //
-// Tables in shared memory, built once per CTA from cubepad_geom.h (cubepad_for_each_copy: the push table
-// inverted): one word per input position (face, y, x) — the staged word of its interior copy, the number of halo
+// Tables in shared memory (cubepad_geom.h, cubepad_for_each_copy: the push table inverted). They depend only on
+// the geometry and the channels per stage, so the launcher keeps one copy per (device, geometry) in device memory —
+// built by a one-CTA launch of this kernel (tab_out) — and every CTA of a normal launch fetches them with one bulk
+// copy (tab); without a cached copy (first sight of a geometry inside a stream capture) every CTA builds them itself.
+// One word per input position (face, y, x) — the staged word of its interior copy, the number of halo
 // positions that copied it and where their list starts — and a short list of 16-bit staged words for the halo
 // copies (only the pixels within a pad width of a face edge have any: 12 % at H = 32). Halo copies are summed in
 // the fixed (entry, u, v) order — the same order as cubepad_bwd_band_kernel, so both paths produce bit-identical,
