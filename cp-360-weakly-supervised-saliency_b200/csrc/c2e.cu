@@ -261,8 +261,7 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
   const int fstride = a.K * ww;                                             // face stride inside a stage
 
   pdl_trigger();
-  auto issue = [&](int i) {                                                  // thread 0: stage i of this CTA
-    const int s = i % a.stages;
+  auto issue = [&](int i, int s) {                                           // thread 0: step i of this CTA into ring slot s = i % stages
     const int c0 = c_begin + i * a.K, kl = min(a.K, c_end - c0);
     const uint32_t bytes = (uint32_t)(kl * ww) * 4u;
     tma::mbar_expect_tx(&full[s], 6u * bytes);
@@ -278,7 +277,7 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
   __syncthreads();
   pdl_wait();
   if (tid == 0)
-    for (int i = 0; i < min(a.stages, n_st); ++i) issue(i);
+    for (int i = 0; i < min(a.stages, n_st); ++i) issue(i, i);
   __syncwarp();
 
   // this thread's pixels: plan entries live in registers for the whole kernel
@@ -312,9 +311,10 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
     }
   }
 
+  int s = 0;                                             // ring slot and phase of step i (no division in the loop)
+  uint32_t ph = 0;
   for (int i = 0; i < n_st; ++i) {
-    const int s = i % a.stages;
-    tma::mbar_wait(&full[s], (uint32_t)((i / a.stages) & 1));
+    tma::mbar_wait(&full[s], ph);
     const int c0 = c_begin + i * a.K, kl = min(a.K, c_end - c0);
     const float* st = ring + (size_t)s * a.stage_floats;
 #pragma unroll
@@ -347,7 +347,8 @@ c2e_max_cluster_kernel(const C2eMaxArgs a) {
     }
     __syncwarp();                                        // reconverge lane 0 (bulk-load issue) before the block barrier
     __syncthreads();                                     // every thread is done with stage s
-    if (tid == 0 && i + a.stages < n_st) issue(i + a.stages);
+    if (tid == 0 && i + a.stages < n_st) issue(i + a.stages, s);
+    if (++s == a.stages) { s = 0; ph ^= 1u; }
   }
 #pragma unroll
   for (int k = 0; k < NPIX; ++k) {
