@@ -64,3 +64,19 @@ def test_b200_arm_has_no_cpu_fallback():
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
     assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())
+
+
+def test_both_arms_name_the_same_workload():
+    """The driver compares the `config.workload` strings of the two arms; the first-site note must follow the flag in both."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    for wl in ("chain", "corpus", "clstm"):
+        for two in (False, True):
+            a = argparse.Namespace(workload=wl, cube=256, clstm_variant="baseline", no_fuse_first_site=two)
+            s = bench.workload_string(a)
+            assert ("one kernel" in s) == (wl != "clstm" and not two), (wl, two, s)
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-frames", "1")
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert line["config"]["workload"] == bench.workload_string(
+        argparse.Namespace(workload="chain", cube=256, clstm_variant="baseline", no_fuse_first_site=False))
