@@ -306,7 +306,8 @@ def test_cubepad_backward_table_cache_and_graph_capture(dev, monkeypatch):
 def test_cubepad_backward_matches_autograd(dev):
     """Backward = transpose of the gather (train_temporal.py:167-170 back-propagates through it)."""
     for shape, pad in [((6, 3, 7, 7), 1), ((12, 4, 8, 8), [2, 1, 1, 3]), ((6, 2, 32, 32), 3), ((6, 5, 9, 9), [4, 2, 3, 5]),
-                       ((12, 2000, 7, 7), 1), ((6, 3, 5, 5), 5), ((6, 2, 56, 56), 1), ((6, 1, 1, 1), 1)]:
+                       ((12, 2000, 7, 7), 1), ((6, 3, 5, 5), 5), ((6, 2, 56, 56), 1), ((6, 1, 1, 1), 1),
+                       ((6, 3, 40, 40), 2), ((12, 2, 64, 64), 1), ((6, 1, 100, 100), 3), ((6, 2, 128, 128), [1, 2, 0, 3])]:
         x = torch.randn(shape, device=dev, dtype=torch.float32, requires_grad=True)
         y = cp360_b200.CubePad(pad)(x)
         gy = torch.randn_like(y)
